@@ -1,0 +1,238 @@
+"""Tensor-level wrappers of the sm_100a kernel library (``skycomputing_b200._cuda``).
+
+Every function validates dtype / layout in Python, then hands raw device pointers and the current
+CUDA stream to the C++ launcher (which is torch-free, see csrc/bindings_cuda.cpp).  Outputs are
+pre-allocated by the caller or allocated here through torch's caching allocator, so everything is
+CUDA-graph capturable.
+
+These wrappers FAIL LOUDLY when the extension is missing on a GPU machine: there is no silent
+PyTorch fallback on the hot path (the eager oracle lives in ``skycomputing_b200.models`` and is
+selected explicitly with ``backend="torch"``).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+_cuda = None
+_import_error: Optional[BaseException] = None
+try:  # the .so is built in-tree by skycomputing_b200._build / __graft_entry__.build()
+    from .. import _cuda as _cuda_mod  # type: ignore
+
+    _cuda = _cuda_mod
+except Exception as e:  # pragma: no cover - exercised only when the build is missing
+    _import_error = e
+
+ACT_NONE, ACT_GELU, ACT_DGELU_MUL_AUX = 0, 1, 2
+
+
+def available() -> bool:
+    """True iff the native extension is importable AND a CUDA device is present."""
+    return _cuda is not None and torch.cuda.is_available()
+
+
+def ext():
+    if _cuda is None:
+        raise RuntimeError(
+            "skycomputing_b200._cuda is not built/importable "
+            f"({_import_error!r}); run `python -m skycomputing_b200._build` "
+            "(or __graft_entry__.build()) first"
+        )
+    return _cuda
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> int:
+    return 0 if t is None else t.data_ptr()
+
+
+def _check(t: torch.Tensor, dtype: torch.dtype, name: str) -> None:
+    if not t.is_cuda:
+        raise ValueError(f"{name} must be a CUDA tensor")
+    if t.dtype != dtype:
+        raise ValueError(f"{name} must be {dtype}, got {t.dtype}")
+    if t.dim() >= 1 and t.stride(-1) != 1:
+        raise ValueError(f"{name} must have a unit inner stride")
+
+
+class RngState:
+    """Device-resident dropout RNG state {seed, step}; ``advance()`` is a captured kernel."""
+
+    def __init__(self, seed: int, device: torch.device | str = "cuda"):
+        # int64 storage, interpreted as uint64 on the device
+        self.state = torch.tensor([int(seed) & 0x7FFFFFFFFFFFFFFF, 0], dtype=torch.int64,
+                                  device=device)
+
+    @property
+    def ptr(self) -> int:
+        return self.state.data_ptr()
+
+    def advance(self, inc: int = 1) -> None:
+        ext().advance_counter(self.state.data_ptr() + 8, inc, _stream())
+
+
+def gemm(
+    a: torch.Tensor,
+    b: torch.Tensor,
+    *,
+    a_mn: bool = False,
+    b_mn: bool = False,
+    out: Optional[torch.Tensor] = None,
+    out_dtype: torch.dtype = torch.bfloat16,
+    accumulate: bool = False,
+    bias: Optional[torch.Tensor] = None,
+    aux: Optional[torch.Tensor] = None,
+    act: int = ACT_NONE,
+    add_aux: bool = False,
+    out2: Optional[torch.Tensor] = None,
+    dropout_p: float = 0.0,
+    rng: Optional[RngState] = None,
+    rng_stream: int = 0,
+    out_ptr: int = 0,
+    out_ld: int = 0,
+    signal_flags: int = 0,
+    wait_flags: int = 0,
+    wait_epoch: int = 0,
+    wait_mult: int = 0,
+    error_flag: int = 0,
+    block_n: int = 0,
+    max_ctas: int = 0,
+) -> Optional[torch.Tensor]:
+    """out[M,N] = epilogue(sum_k A[m,k] B[n,k]) on the tcgen05 kernel.
+
+    ``a``: [M,K] (or [K,M] when ``a_mn``); ``b``: [N,K] (or [K,N] when ``b_mn``), both bf16 with
+    unit inner stride.  ``out_ptr``/``out_ld`` redirect the store to a raw (peer) pointer.
+    """
+    _check(a, torch.bfloat16, "a")
+    _check(b, torch.bfloat16, "b")
+    if a.dim() != 2 or b.dim() != 2:
+        raise ValueError("gemm operands must be 2-D")
+    if a_mn:
+        K, M = a.shape
+    else:
+        M, K = a.shape
+    if b_mn:
+        Kb, N = b.shape
+    else:
+        N, Kb = b.shape
+    if K != Kb:
+        raise ValueError(f"inner dimensions differ: {K} vs {Kb}")
+    out_f32 = out_dtype == torch.float32 if out is None else out.dtype == torch.float32
+    if out_ptr:
+        o_ptr, ldo = out_ptr, out_ld
+    else:
+        if out is None:
+            out = torch.empty((M, N), dtype=out_dtype, device=a.device)
+        _check(out, torch.float32 if out_f32 else torch.bfloat16, "out")
+        if tuple(out.shape) != (M, N):
+            raise ValueError(f"out has shape {tuple(out.shape)}, expected {(M, N)}")
+        o_ptr, ldo = out.data_ptr(), out.stride(0)
+    if bias is not None:
+        _check(bias, torch.float32, "bias")
+    if aux is not None:
+        _check(aux, torch.bfloat16, "aux")
+    if out2 is not None:
+        _check(out2, torch.bfloat16, "out2")
+    ext().gemm(
+        A=a.data_ptr(), B=b.data_ptr(), M=M, N=N, K=K, lda=a.stride(0), ldb=b.stride(0),
+        a_mn=a_mn, b_mn=b_mn, out=o_ptr, ldo=ldo, out_f32=out_f32, accumulate=accumulate,
+        out2=_ptr(out2), ldo2=0 if out2 is None else out2.stride(0), bias=_ptr(bias),
+        aux=_ptr(aux), ldaux=0 if aux is None else aux.stride(0), act=act, add_aux=add_aux,
+        dropout_p=float(dropout_p), rng_state=0 if rng is None else rng.ptr,
+        rng_stream=rng_stream, signal_flags=signal_flags, wait_flags=wait_flags,
+        wait_epoch=wait_epoch, wait_mult=wait_mult, error_flag=error_flag, block_n=block_n,
+        max_ctas=max_ctas, stream=_stream(),
+    )
+    return out
+
+
+def layernorm_fwd(z, gamma, beta, eps: float = 1e-12, *, y=None, wait_flags: int = 0,
+                  wait_epoch: int = 0, wait_mult: int = 0, error_flag: int = 0):
+    _check(z, torch.bfloat16, "z")
+    M, H = z.shape
+    if not z.is_contiguous():
+        raise ValueError("z must be contiguous")
+    y = torch.empty_like(z) if y is None else y
+    mean = torch.empty(M, dtype=torch.float32, device=z.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=z.device)
+    ext().layernorm_fwd(z=z.data_ptr(), y=y.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr(),
+                        gamma=gamma.data_ptr(), beta=beta.data_ptr(), M=M, H=H, eps=eps,
+                        wait_flags=wait_flags, wait_epoch=wait_epoch, wait_mult=wait_mult,
+                        error_flag=error_flag, stream=_stream())
+    return y, mean, rstd
+
+
+def layernorm_bwd(dy, z, mean, rstd, gamma, dgamma, dbeta, *, dropout_p: float = 0.0,
+                  rng: Optional[RngState] = None, rng_stream: int = 0, wait_flags: int = 0,
+                  wait_epoch: int = 0, wait_mult: int = 0, error_flag: int = 0):
+    """Returns (dz, dz_dropped or None); dgamma/dbeta (fp32) are accumulated in place."""
+    _check(dy, torch.bfloat16, "dy")
+    _check(z, torch.bfloat16, "z")
+    M, H = z.shape
+    dz = torch.empty_like(z)
+    dzd = torch.empty_like(z) if dropout_p > 0 else None
+    ext().layernorm_bwd(dy=dy.data_ptr(), z=z.data_ptr(), mean=mean.data_ptr(),
+                        rstd=rstd.data_ptr(), gamma=gamma.data_ptr(), dz=dz.data_ptr(),
+                        dz_dropped=_ptr(dzd), dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(),
+                        M=M, H=H, dropout_p=float(dropout_p),
+                        rng_state=0 if rng is None else rng.ptr, rng_stream=rng_stream,
+                        wait_flags=wait_flags, wait_epoch=wait_epoch, wait_mult=wait_mult,
+                        error_flag=error_flag, stream=_stream())
+    return dz, dzd
+
+
+def colsum_(x: torch.Tensor, out: torch.Tensor) -> None:
+    """out[n] += sum_m x[m, n]  (x bf16, out fp32)."""
+    _check(x, torch.bfloat16, "x")
+    _check(out, torch.float32, "out")
+    M, N = x.shape
+    ext().colsum(x=x.data_ptr(), M=M, N=N, ldx=x.stride(0), out=out.data_ptr(), stream=_stream())
+
+
+def attention_fwd(qkv, mask, B: int, S: int, heads: int, *, dropout_p: float = 0.0,
+                  rng: Optional[RngState] = None, rng_stream: int = 0):
+    _check(qkv, torch.bfloat16, "qkv")
+    H = qkv.shape[1] // 3
+    d = H // heads
+    ctx = torch.empty((B * S, H), dtype=torch.bfloat16, device=qkv.device)
+    lse = torch.empty((B * heads * S,), dtype=torch.float32, device=qkv.device)
+    ext().attention_fwd(qkv=qkv.data_ptr(), mask=_ptr(mask), ctx=ctx.data_ptr(),
+                        lse=lse.data_ptr(), B=B, S=S, heads=heads, head_dim=d,
+                        scale=1.0 / (d ** 0.5), dropout_p=float(dropout_p),
+                        rng_state=0 if rng is None else rng.ptr, rng_stream=rng_stream,
+                        stream=_stream())
+    return ctx, lse
+
+
+def attention_bwd(qkv, mask, ctx, lse, dctx, B: int, S: int, heads: int, *,
+                  dropout_p: float = 0.0, rng: Optional[RngState] = None, rng_stream: int = 0):
+    _check(dctx, torch.bfloat16, "dctx")
+    if not dctx.is_contiguous():
+        dctx = dctx.contiguous()
+    H = qkv.shape[1] // 3
+    d = H // heads
+    dqkv = torch.empty_like(qkv)
+    ext().attention_bwd(qkv=qkv.data_ptr(), mask=_ptr(mask), ctx=ctx.data_ptr(),
+                        lse=lse.data_ptr(), dctx=dctx.data_ptr(), dqkv=dqkv.data_ptr(), B=B, S=S,
+                        heads=heads, head_dim=d, scale=1.0 / (d ** 0.5),
+                        dropout_p=float(dropout_p), rng_state=0 if rng is None else rng.ptr,
+                        rng_stream=rng_stream, stream=_stream())
+    return dqkv
+
+
+def cast_f32_to_bf16_(src: torch.Tensor, dst: torch.Tensor) -> None:
+    ext().cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
+
+
+def softmax_ce(logits: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0):
+    _check(logits, torch.float32, "logits")
+    M, C = logits.shape
+    loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+    dlogits = torch.empty_like(logits)
+    ext().softmax_ce(logits=logits.data_ptr(), labels=labels.data_ptr(), loss=loss.data_ptr(),
+                     dlogits=dlogits.data_ptr(), M=M, C=C, grad_scale=grad_scale, stream=_stream())
+    return loss, dlogits

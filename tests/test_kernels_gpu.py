@@ -1,0 +1,240 @@
+"""Numerics of every sm_100a kernel against a plain PyTorch fp32 reference of the same op."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nat():
+    from skycomputing_b200.ops import native
+
+    assert native.available(), "native extension must be built and a GPU present"
+    return native
+
+
+def _rand(*shape, scale=1.0, dtype=torch.bfloat16):
+    return (torch.randn(*shape, device="cuda", dtype=torch.float32) * scale).to(dtype)
+
+
+def _close(got, ref, rtol=2e-2, atol=2e-2):
+    got = got.float()
+    ref = ref.float()
+    err = (got - ref).abs().max().item()
+    denom = ref.abs().max().item() + 1e-6
+    assert torch.isfinite(got).all(), "non-finite output"
+    assert err <= atol + rtol * denom, f"max abs err {err} vs ref max {denom}"
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+@pytest.mark.parametrize("M,N,K", [(256, 512, 320), (200, 264, 64), (1024, 1024, 1024), (32, 1024, 1024)])
+def test_gemm_kk(nat, M, N, K, block_n):
+    torch.manual_seed(0)
+    a, b = _rand(M, K), _rand(N, K)
+    bias = torch.randn(N, device="cuda")
+    out = nat.gemm(a, b, bias=bias, block_n=block_n)
+    ref = a.float() @ b.float().t() + bias
+    _close(out, ref, atol=0.05 * math.sqrt(K) / 8)
+
+
+def test_gemm_strided_views(nat):
+    torch.manual_seed(1)
+    big = _rand(512, 3 * 256)
+    a = big[:, 256:512]  # row stride 768, inner stride 1
+    b = _rand(384, 256)
+    out = nat.gemm(a, b)
+    _close(out, a.float() @ b.float().t(), atol=0.2)
+
+
+def test_gemm_gelu_dual_output(nat):
+    torch.manual_seed(2)
+    M, N, K = 384, 768, 256
+    a, b = _rand(M, K), _rand(N, K, scale=0.1)
+    bias = torch.randn(N, device="cuda") * 0.1
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    out = nat.gemm(a, b, bias=bias, act=nat.ACT_GELU, out2=pre)
+    h = a.float() @ b.float().t() + bias
+    _close(pre, h)
+    _close(out, h * 0.5 * (1.0 + torch.erf(h / math.sqrt(2.0))))
+
+
+def test_gemm_residual_and_dgelu(nat):
+    torch.manual_seed(3)
+    M, N, K = 256, 512, 512
+    a, b = _rand(M, K, scale=0.2), _rand(N, K, scale=0.2)
+    aux = _rand(M, N)
+    out = nat.gemm(a, b, aux=aux, add_aux=True)
+    _close(out, a.float() @ b.float().t() + aux.float())
+    out = nat.gemm(a, b, aux=aux, act=nat.ACT_DGELU_MUL_AUX)
+    x = aux.float()
+    dg = 0.5 * (1 + torch.erf(x / math.sqrt(2))) + x * torch.exp(-0.5 * x * x) / math.sqrt(2 * math.pi)
+    _close(out, (a.float() @ b.float().t()) * dg)
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_dgrad_layout(nat, block_n):
+    """dX[M,K] = dY[M,N] W[N,K]: A K-major, B MN-major (no transposed weight copy)."""
+    torch.manual_seed(4)
+    M, N, K = 384, 320, 512  # reduction over N
+    dy, w = _rand(M, N), _rand(N, K, scale=0.2)
+    out = nat.gemm(dy, w, b_mn=True, block_n=block_n)
+    _close(out, dy.float() @ w.float(), atol=0.2)
+
+
+@pytest.mark.parametrize("block_n", [128, 256])
+def test_gemm_wgrad_layout_f32_accumulate(nat, block_n):
+    """dW[N,K] (+)= dY^T[N,M] X[M,K]: both operands MN-major, fp32 output with accumulation."""
+    torch.manual_seed(5)
+    M, N, K = 640, 384, 512  # reduction over M (tokens)
+    dy, x = _rand(M, N, scale=0.3), _rand(M, K, scale=0.3)
+    dw = torch.ones(N, K, device="cuda", dtype=torch.float32)
+    nat.gemm(dy, x, a_mn=True, b_mn=True, out=dw, accumulate=True, block_n=block_n)
+    _close(dw, 1.0 + dy.float().t() @ x.float(), rtol=1e-2, atol=0.05)
+    dw2 = nat.gemm(dy, x, a_mn=True, b_mn=True, out_dtype=torch.float32, block_n=block_n)
+    _close(dw2, dy.float().t() @ x.float(), rtol=1e-2, atol=0.05)
+
+
+def test_gemm_dropout_mask_consistent_with_layernorm_bwd(nat):
+    torch.manual_seed(6)
+    M, H = 256, 1024
+    rng = nat.RngState(1234)
+    a = torch.zeros(M, 64, dtype=torch.bfloat16, device="cuda")
+    b = torch.zeros(H, 64, dtype=torch.bfloat16, device="cuda")
+    ones = torch.ones(H, device="cuda")
+    p = 0.1
+    out = nat.gemm(a, b, bias=ones, dropout_p=p, rng=rng, rng_stream=7).float()
+    keep = out != 0
+    frac = keep.float().mean().item()
+    assert abs(frac - (1 - p)) < 0.01, frac
+    _close(out[keep], torch.full_like(out[keep], 1 / (1 - p)))
+    # LayerNorm backward must regenerate the identical mask for dz_dropped
+    z = _rand(M, H)
+    dy = _rand(M, H)
+    gamma = torch.ones(H, device="cuda")
+    beta = torch.zeros(H, device="cuda")
+    _, mean, rstd = nat.layernorm_fwd(z, gamma, beta)
+    dg = torch.zeros(H, device="cuda")
+    db = torch.zeros(H, device="cuda")
+    dz, dzd = nat.layernorm_bwd(dy, z, mean, rstd, gamma, dg, db, dropout_p=p, rng=rng, rng_stream=7)
+    expect = torch.where(keep, dz.float() / (1 - p), torch.zeros_like(dz.float()))
+    _close(dzd, expect)
+    # a different step gives a different mask
+    rng.advance()
+    out2 = nat.gemm(a, b, bias=ones, dropout_p=p, rng=rng, rng_stream=7).float()
+    assert ((out2 != 0) != keep).float().mean().item() > 0.05
+
+
+@pytest.mark.parametrize("H", [64, 256, 1024])
+def test_layernorm_fwd_bwd(nat, H):
+    torch.manual_seed(7)
+    M = 300
+    z = _rand(M, H, scale=2.0)
+    gamma = torch.randn(H, device="cuda") * 0.5 + 1
+    beta = torch.randn(H, device="cuda") * 0.1
+    y, mean, rstd = nat.layernorm_fwd(z, gamma, beta, 1e-12)
+    zf = z.float().requires_grad_(True)
+    g = gamma.clone().requires_grad_(True)
+    bt = beta.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(zf, (H,), g, bt, 1e-12)
+    _close(y, ref)
+    dy = _rand(M, H)
+    ref.backward(dy.float())
+    dg = torch.zeros(H, device="cuda")
+    db = torch.zeros(H, device="cuda")
+    dz, _ = nat.layernorm_bwd(dy, z, mean, rstd, gamma, dg, db)
+    _close(dz, zf.grad)
+    _close(dg, g.grad, rtol=2e-2, atol=0.3)
+    _close(db, bt.grad, rtol=2e-2, atol=0.3)
+
+
+def test_colsum(nat):
+    x = _rand(1000, 768)
+    out = torch.ones(768, device="cuda")
+    nat.colsum_(x, out)
+    _close(out, 1 + x.float().sum(0), rtol=1e-3, atol=1e-2)
+
+
+def _attention_ref(qkv, mask, B, S, heads):
+    H = qkv.shape[1] // 3
+    d = H // heads
+    q, k, v = qkv.float().view(B, S, 3, heads, d).permute(2, 0, 3, 1, 4)
+    s = q @ k.transpose(-1, -2) / math.sqrt(d)
+    if mask is not None:
+        s = s + mask.view(B, 1, 1, S)
+    p = torch.softmax(s, -1)
+    o = p @ v
+    return o.permute(0, 2, 1, 3).reshape(B * S, H)
+
+
+@pytest.mark.parametrize("with_mask", [False, True])
+def test_attention_fwd_bwd(nat, with_mask):
+    torch.manual_seed(8)
+    B, S, heads, d = 3, 128, 4, 64
+    H = heads * d
+    qkv = _rand(B * S, 3 * H)
+    mask = None
+    if with_mask:
+        m = torch.ones(B, S, device="cuda")
+        m[0, 100:] = 0
+        m[2, 17:] = 0
+        mask = (1.0 - m) * -10000.0
+    ctx, lse = nat.attention_fwd(qkv, mask, B, S, heads)
+    qf = qkv.float().requires_grad_(True)
+    ref = _attention_ref(qf, mask, B, S, heads)
+    _close(ctx, ref)
+    dctx = _rand(B * S, H)
+    ref.backward(dctx.float())
+    dqkv = nat.attention_bwd(qkv, mask, ctx, lse, dctx, B, S, heads)
+    _close(dqkv, qf.grad, rtol=3e-2, atol=3e-2)
+
+
+def test_attention_dropout_statistics(nat):
+    torch.manual_seed(9)
+    B, S, heads, d = 2, 128, 2, 64
+    H = heads * d
+    qkv = torch.zeros(B * S, 3 * H, dtype=torch.bfloat16, device="cuda")
+    qkv[:, 2 * H:] = 1.0  # V = 1 -> ctx = sum_j P_ij keep_ij / (1-p) ~ 1
+    rng = nat.RngState(77)
+    ctx, _ = nat.attention_fwd(qkv, None, B, S, heads, dropout_p=0.1, rng=rng, rng_stream=3)
+    c = ctx.float()
+    assert abs(c.mean().item() - 1.0) < 0.02
+    assert 0.01 < c.std().item() < 0.1
+
+
+def test_softmax_ce(nat):
+    torch.manual_seed(10)
+    logits = torch.randn(32, 3, device="cuda")
+    labels = torch.randint(0, 3, (32,), device="cuda")
+    loss, dl = nat.softmax_ce(logits, labels)
+    lf = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lf, labels)
+    ref.backward()
+    _close(loss, ref.detach().view(1), rtol=1e-4, atol=1e-5)
+    _close(dl, lf.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_gemm_flag_handshake_single_gpu(nat):
+    """Consumer GEMM launched FIRST on a side stream must wait for the producer's panel flags."""
+    torch.manual_seed(11)
+    M, H, I = 512, 256, 512
+    x, w1, w2 = _rand(M, H), _rand(I, H, scale=0.1), _rand(H, I, scale=0.1)
+    mid = torch.zeros(M, I, dtype=torch.bfloat16, device="cuda")
+    flags = torch.zeros(M // 128, dtype=torch.int32, device="cuda")
+    epoch = torch.ones(1, dtype=torch.int32, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    out = torch.empty(M, H, dtype=torch.bfloat16, device="cuda")
+    bn = 128
+    tiles = nat.ext().gemm_tiles_per_panel(I, bn)
+    torch.cuda.synchronize()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        nat.gemm(mid, w2, out=out, wait_flags=flags.data_ptr(), wait_epoch=epoch.data_ptr(),
+                 wait_mult=tiles, error_flag=err.data_ptr(), max_ctas=8)
+    nat.gemm(x, w1, out=mid, signal_flags=flags.data_ptr(), block_n=bn, max_ctas=16)
+    torch.cuda.synchronize()
+    assert err.item() == 0
+    assert flags.tolist() == [tiles] * (M // 128)
+    ref_mid = (x.float() @ w1.float().t()).to(torch.bfloat16)
+    _close(out, ref_mid.float() @ w2.float().t(), atol=0.1)
