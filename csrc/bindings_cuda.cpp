@@ -81,8 +81,9 @@ void gemm(uintptr_t A, uintptr_t B, int M, int N, int K, int lda, int ldb, bool 
 void layernorm_fwd(uintptr_t z, uintptr_t y, uintptr_t mean, uintptr_t rstd, uintptr_t gamma,
                    uintptr_t beta, int M, int H, float eps, uintptr_t wait_flags,
                    uintptr_t wait_epoch, uint32_t wait_mult, uintptr_t error_flag,
-                   uintptr_t stream) {
+                   uintptr_t signal_flags, uintptr_t stream) {
   sky::LayerNormFwdArgs a;
+  a.signal_flags = P<uint32_t>(signal_flags);
   a.z = P<void>(z);
   a.y = P<void>(y);
   a.mean = P<float>(mean);
@@ -359,7 +360,13 @@ PYBIND11_MODULE(_cuda, m) {
   m.def("layernorm_fwd", &layernorm_fwd, py::arg("z"), py::arg("y"), py::arg("mean"),
         py::arg("rstd"), py::arg("gamma"), py::arg("beta"), py::arg("M"), py::arg("H"),
         py::arg("eps"), py::arg("wait_flags") = 0, py::arg("wait_epoch") = 0,
-        py::arg("wait_mult") = 0, py::arg("error_flag") = 0, py::arg("stream") = 0);
+        py::arg("wait_mult") = 0, py::arg("error_flag") = 0, py::arg("signal_flags") = 0,
+        py::arg("stream") = 0);
+  m.attr("LN_SIGNALS_PER_PANEL") = sky::kLnSignalsPerPanel;
+  m.def("dgelu_mul", [](uintptr_t g, uintptr_t h, uintptr_t y, long long n, uintptr_t s) {
+    check(sky::launch_dgelu_mul(P<const void>(g), P<const void>(h), P<void>(y), n, S(s)),
+          "dgelu_mul");
+  });
   m.def("layernorm_bwd", &layernorm_bwd, py::arg("dy"), py::arg("z"), py::arg("mean"),
         py::arg("rstd"), py::arg("gamma"), py::arg("dz"), py::arg("dz_dropped") = 0,
         py::arg("dgamma"), py::arg("dbeta"), py::arg("M"), py::arg("H"),

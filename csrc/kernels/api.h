@@ -72,7 +72,11 @@ struct LayerNormFwdArgs {
   const uint32_t* wait_epoch = nullptr;
   uint32_t wait_mult = 0;
   int* error_flag = nullptr;
+  // optional: y is (peer) boundary memory; every CTA (32 rows) bumps signal_flags[row/128] once
+  // with release.sys, i.e. a 128-row panel is complete at 4 signals (kLnSignalsPerPanel)
+  uint32_t* signal_flags = nullptr;
 };
+constexpr int kLnSignalsPerPanel = 4;
 int launch_layernorm_fwd(const LayerNormFwdArgs& a, cudaStream_t stream);
 
 struct LayerNormBwdArgs {
@@ -95,6 +99,9 @@ struct LayerNormBwdArgs {
   int* error_flag = nullptr;
 };
 int launch_layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t stream);
+
+// y[i] = g[i] * gelu'(h[i])  (bf16, n % 8 == 0): only used when a stage cut separates FFN1 | FFN2
+int launch_dgelu_mul(const void* g, const void* h, void* y, long long n, cudaStream_t stream);
 
 // column sums: out[n] += sum_m x[m,n]   (bias gradients)
 int launch_colsum(const void* x_bf16, int M, int N, int ldx, float* out, cudaStream_t stream);

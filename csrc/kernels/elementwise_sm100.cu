@@ -44,6 +44,7 @@ __device__ __forceinline__ void warp_wait_panel(const uint32_t* flags, int panel
 // H % 8 == 0, H <= 2048.  NV = number of 16B vectors per lane (compile-time).
 // ------------------------------------------------------------------------------------------
 constexpr int kLnMaxVec = 8;  // H <= 8*256
+constexpr int kLnRowsPerCta = 32;  // 128-row panel = 4 signals
 
 template <int NV>
 __global__ void __launch_bounds__(256)
@@ -51,17 +52,20 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restr
                      float* __restrict__ mean_out, float* __restrict__ rstd_out,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int M, int H,
                      float eps, const uint32_t* wait_flags, const uint32_t* wait_epoch,
-                     uint32_t wait_mult, int* error_flag) {
+                     uint32_t wait_mult, int* error_flag, uint32_t* signal_flags) {
+  // Each CTA owns kLnRowsPerCta consecutive rows (8 warps x 4 rows) so that a finished CTA can
+  // publish "32 rows of panel p are written" with one release.sys add (y may be peer memory).
   const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
-  const int total_warps = gridDim.x * warps_per_block;
+  const int warp = threadIdx.x >> 5;
   const int nvec = H / 8;  // 16B vectors per row
   const float inv_h = 1.f / static_cast<float>(H);
   const uint32_t target = wait_flags ? (*wait_epoch) * wait_mult : 0u;
   int last_panel = -1;
+  const int row_base = blockIdx.x * kLnRowsPerCta;
 
-  for (int row = warp_global; row < M; row += total_warps) {
+  for (int r = warp; r < kLnRowsPerCta; r += 8) {
+    const int row = row_base + r;
+    if (row >= M) break;
     if (wait_flags != nullptr) {
       const int panel = row >> 7;
       if (panel != last_panel) {
@@ -123,6 +127,11 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restr
         yr[v] = o;
       }
     }
+  }
+  if (signal_flags != nullptr) {
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) red_release_sys_add(signal_flags + (row_base >> 7), 1u);
   }
 }
 
@@ -742,6 +751,26 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float*
     d[i] = __bfloat162float(s[i]);
 }
 
+__global__ void __launch_bounds__(256)
+dgelu_mul_kernel(const uint4* __restrict__ g, const uint4* __restrict__ h, uint4* __restrict__ y,
+                 long long n8) {
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const uint4 a = g[i];
+    const uint4 b = h[i];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+    const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const float2 x = unpack_bf16x2(aw[t]);
+      const float2 z = unpack_bf16x2(bw[t]);
+      o[t] = pack_bf16x2(x.x * dgelu_erf(z.x), x.y * dgelu_erf(z.y));
+    }
+    y[i] = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // runtime helpers
 // ------------------------------------------------------------------------------------------
@@ -804,13 +833,13 @@ inline int grid_for_rows(int rows, int warps_per_block, int max_blocks) {
 int launch_layernorm_fwd(const LayerNormFwdArgs& a, cudaStream_t stream) {
   if (a.M <= 0) return 0;
   if (a.H % 8 != 0 || a.H > kLnMaxVec * 256) return 910;
-  const int grid = grid_for_rows(a.M, 8, 148 * 8);
+  const int grid = (a.M + kLnRowsPerCta - 1) / kLnRowsPerCta;
   const int nv = (a.H / 8 + 31) / 32;
 #define SKY_LN_FWD(NV)                                                                          \
   layernorm_fwd_kernel<NV><<<grid, 256, 0, stream>>>(                                           \
       reinterpret_cast<const __nv_bfloat16*>(a.z), reinterpret_cast<__nv_bfloat16*>(a.y), a.mean, \
       a.rstd, a.gamma, a.beta, a.M, a.H, a.eps, a.wait_flags, a.wait_epoch, a.wait_mult,        \
-      a.error_flag)
+      a.error_flag, a.signal_flags)
   if (nv <= 1) SKY_LN_FWD(1);
   else if (nv <= 2) SKY_LN_FWD(2);
   else if (nv <= 4) SKY_LN_FWD(4);
@@ -848,6 +877,17 @@ int launch_layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t stream) {
                                                  reinterpret_cast<const __nv_bfloat16*>(a.z),
                                                  a.mean, a.rstd, a.dgamma, a.dbeta, a.M, a.H);
   }
+  SKY_LAUNCH_CHECK();
+}
+
+int launch_dgelu_mul(const void* g, const void* h, void* y, long long n, cudaStream_t stream) {
+  if (n <= 0) return 0;
+  if (n % 8 != 0) return 914;
+  long long blocks = (n / 8 + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  dgelu_mul_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+      reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(h),
+      reinterpret_cast<uint4*>(y), n / 8);
   SKY_LAUNCH_CHECK();
 }
 

@@ -1,0 +1,25 @@
+"""skycomputing_b200 - B200-native load-balanced pipeline-model-parallel training.
+
+Same user-facing surface as hpcaitech/SkyComputing (``scaelum``): python-file configs, the four
+registries, builders, ``dynamics`` (Allocator / benchmarkers / Estimator / ParameterServer /
+Worker / WorkerManager), ``RpcModel``, ``Runner`` + hooks, ``Logger``, ``DistributedTimer``,
+``Stimulator`` - on a Blackwell-first substrate (one process per GPU, hand-written sm_100a
+kernels, peer-memory fused stage boundaries over NVLink 5, C++ allocator / benchmark loop).
+"""
+from .builder import *  # noqa: F401,F403
+from .config import *  # noqa: F401,F403
+from .dataset import *  # noqa: F401,F403
+from .dynamics import *  # noqa: F401,F403
+from .logger import *  # noqa: F401,F403
+from .models import *  # noqa: F401,F403
+from .parallel import (BaseModule, FusedSGD, LocalModule, PipelineEngine, RemoteModule,  # noqa: F401
+                       RpcModel, build_optimizer)
+from .registry import *  # noqa: F401,F403
+from .runner import *  # noqa: F401,F403
+from .stimulator import Stimulator  # noqa: F401
+from .timer import *  # noqa: F401,F403
+from .version import __version__  # noqa: F401
+from . import utils  # noqa: F401
+
+# `scaelum.model` is spelled `models` here; keep the old name importable
+from . import models as model  # noqa: F401,E402

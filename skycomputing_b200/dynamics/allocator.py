@@ -1,0 +1,169 @@
+"""Layer -> device allocation front-end (``Allocator``).
+
+Same public surface as scaelum/dynamics/allocator.py:12-439 - ``even_allocate()``,
+``dynamic_allocate(break_iter=1000)``, ``optimal_allocate(max_time=300, threads=24)``, all
+returning the (re-ranked) ``WorkerManager`` - on top of the C++ core (csrc/alloc/allocator.cc):
+
+* ``even``     pure arithmetic, identical split to the reference;
+* ``dynamic``  greedy boundary shifting after a memory pass; ``solver="compat"`` reproduces the
+               reference bit-for-bit (including the dead shrink branch),
+               the default ``"heuristic"`` runs the intended two-way refinement;
+* ``optimal``  exact min-max contiguous partition (bisection + subset DP over device orders)
+               instead of a time-limited MILP (PuLP/CBC are not even installable here);
+               ``max_time`` / ``threads`` are accepted for API compatibility and ignored - the
+               exact solver needs milliseconds for D = 8, L = 483.
+
+Extras (all optional): ``granularity="block"`` only cuts between whole transformer blocks (the
+fused NVLink boundary exists for those cuts and they carry 5x less data than a cut after
+``BertLayer_Body``); ``comm_aware=True`` adds boundary-bytes / link-bandwidth to the stage cost.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, List, Optional, Sequence
+
+from .. import _core
+from .worker_manager import WorkerManager
+
+_BLOCK_SEQ = ("BertLayer_Head", "BertLayer_Body", "BertLayer_Tail")
+
+
+def group_units(model_cfg: Sequence[dict], granularity: str) -> List[tuple]:
+    """[(begin, end)] index ranges of the allocatable units of the layer list."""
+    n = len(model_cfg)
+    if granularity == "layer":
+        return [(i, i + 1) for i in range(n)]
+    units, i = [], 0
+    while i < n:
+        names = [c.get("layer_type") for c in model_cfg[i:i + 3]]
+        if tuple(names) == _BLOCK_SEQ:
+            units.append((i, i + 3))
+            i += 3
+        else:
+            units.append((i, i + 1))
+            i += 1
+    return units
+
+
+class Allocator:
+    def __init__(self, model_cfg: list, worker_manager: WorkerManager, model_benchmarker=None,
+                 device_benchmarker=None, solver: str = "heuristic", granularity: str = "layer",
+                 comm_aware: bool = False, boundary_bytes: Optional[Sequence[float]] = None,
+                 link_bytes_per_s: float = 770e9, device_flops_per_s: float = 7e14,
+                 logger=None):
+        assert solver in ("heuristic", "compat", "exact"), solver
+        assert granularity in ("layer", "block"), granularity
+        self._model_cfg = model_cfg
+        self._worker_manager = worker_manager
+        self._model_benchmarker = model_benchmarker
+        self._device_benchmarker = device_benchmarker
+        self._solver = solver
+        self._granularity = granularity
+        self._comm_aware = comm_aware
+        self._boundary_bytes = boundary_bytes
+        self._link_bytes_per_s = link_bytes_per_s
+        self._device_flops_per_s = device_flops_per_s
+        self._logger = logger
+        self.last_result: Optional[dict] = None
+
+    # ------------------------------------------------------------------ helpers
+    def _log(self, msg: str) -> None:
+        if self._logger is not None:
+            self._logger.info(msg)
+
+    def _benchmarks(self):
+        results = self._device_benchmarker.benchmark()
+        names = list(results.keys())
+        ranks = [int(n.replace("worker", "")) for n in names]
+        dt = [float(results[n]["time"]) for n in names]
+        dm = [float(results[n]["avai_mem"]) for n in names]
+        lf, lm = self._model_benchmarker.benchmark()
+        lf, lm = [float(x) for x in lf], [float(x) for x in lm]
+        self._log("worker ranks: {}".format(ranks))
+        self._log("worker time: {}".format(dt))
+        return ranks, dt, dm, lf, lm
+
+    def _unit_vectors(self, lf, lm):
+        units = group_units(self._model_cfg, self._granularity)
+        uf = [sum(lf[b:e]) for b, e in units]
+        um = [sum(lm[b:e]) for b, e in units]
+        return units, uf, um
+
+    def _cut_penalty(self, units, dt, uf) -> List[float]:
+        if not (self._comm_aware and self._boundary_bytes is not None):
+            return []
+        # cost unit = dev_time x flops.  The fastest device (dev_time = tmin) sustains
+        # `device_flops_per_s`, so one second == tmin * device_flops_per_s cost units.
+        tmin = min(dt)
+        pen = [0.0] * (len(units) + 1)
+        for k in range(1, len(units)):
+            layer_idx = units[k][0]
+            seconds = float(self._boundary_bytes[layer_idx]) / self._link_bytes_per_s
+            pen[k] = seconds * self._device_flops_per_s * tmin
+        return pen
+
+    def _assign(self, order: Sequence[int], unit_bounds: Sequence[int], units) -> WorkerManager:
+        """order[k] = index (in the current pool) of the worker that runs pipeline stage k."""
+        pool = list(self._worker_manager.worker_pool)
+        n_units = len(units)
+        for k, widx in enumerate(order):
+            ub, ue = unit_bounds[k], unit_bounds[k + 1]
+            b = units[ub][0] if ub < n_units else len(self._model_cfg)
+            e = units[ue - 1][1] if ue > ub else b
+            w = pool[widx]
+            w.model_config = self._model_cfg[b:e]
+            w.layer_range = (b, e)
+            w.order = k + 1
+        self._worker_manager.reset_rank_by_order()
+        for w in self._worker_manager.worker_pool:
+            self._log("rank {} (device {}) has layers {} to {}".format(
+                w.rank, w.device, w.layer_range[0], w.layer_range[1]))
+        return self._worker_manager
+
+    # ------------------------------------------------------------------ public API
+    def even_allocate(self) -> WorkerManager:
+        units = group_units(self._model_cfg, self._granularity)
+        D = self._worker_manager.size
+        bounds = _core.even_partition(len(units), D)
+        self.last_result = dict(method="even", boundaries=bounds, order=list(range(D)))
+        return self._assign(list(range(D)), bounds, units)
+
+    def dynamic_allocate(self, break_iter: int = 1000) -> WorkerManager:
+        ranks, dt, dm, lf, lm = self._benchmarks()
+        units, uf, um = self._unit_vectors(lf, lm)
+        if self._solver == "exact":
+            res = _core.optimal_partition(uf, um, dt, dm, permute=False, min_layers=1,
+                                          cut_penalty=self._cut_penalty(units, dt, uf))
+        else:
+            res = _core.dynamic_partition(uf, um, dt, dm, break_iter=break_iter,
+                                          compat=(self._solver == "compat"),
+                                          cut_penalty=[] if self._solver == "compat"
+                                          else self._cut_penalty(units, dt, uf))
+        self.last_result = res
+        self._log("dynamic allocation: {}".format(res))
+        return self._assign(res["order"], res["boundaries"], units)
+
+    def optimal_allocate(self, max_time: int = 300, threads: int = 24,
+                         permute: bool = True) -> WorkerManager:
+        del max_time, threads  # the exact solver does not need a time limit
+        ranks, dt, dm, lf, lm = self._benchmarks()
+        units, uf, um = self._unit_vectors(lf, lm)
+        res = _core.optimal_partition(uf, um, dt, dm, permute=permute, min_layers=1,
+                                      cut_penalty=self._cut_penalty(units, dt, uf))
+        self.last_result = res
+        self._log("optimal allocation: {}".format(res))
+        return self._assign(res["order"], res["boundaries"], units)
+
+    def allocate(self, alloc_type: str, **kwargs) -> WorkerManager:
+        """Dispatch on ``allocator_config['type']`` (experiment/launch.py:119-138 semantics)."""
+        if alloc_type == "dynamic":
+            return self.dynamic_allocate(**kwargs)
+        if alloc_type == "optimal":
+            return self.optimal_allocate(**kwargs)
+        return self.even_allocate()
+
+    # ------------------------------------------------------------------ diagnostics
+    @staticmethod
+    def bottleneck(layer_flops, layer_mem, dev_time, dev_mem, order, boundaries) -> float:
+        return _core.partition_bottleneck(list(layer_flops), list(layer_mem), list(dev_time),
+                                          list(dev_mem), list(order), list(boundaries))

@@ -1,0 +1,520 @@
+"""Autograd functions that run the BERT layer library on the sm_100a kernels.
+
+One ``torch.autograd.Function`` per *span* of registered layers, so a whole transformer block
+(Head + Body + Tail of the reference's layer list) is 7 forward and ~17 backward kernel launches
+with no framework work in between; spans that are cut by a stage boundary (Head | Body | Tail
+alone or pairs) run the corresponding subset.
+
+Conventions
+-----------
+* activations are bf16 ``[B, S, H]`` (viewed as ``[B*S, H]``), parameters are fp32 masters with
+  bf16 shadows (``ParamBank``); weight/bias gradients are accumulated by the kernels straight into
+  the fp32 ``.grad`` buffers (wgrad GEMM epilogue / colsum / LN param-grad kernels), so autograd
+  receives ``None`` for every parameter input;
+* dropout masks are never stored: every site has an RNG stream id and the backward kernels
+  regenerate the forward mask from ``{seed, step}`` kept in device memory;
+* stage-boundary fusion: ``in_ch`` / ``out_ch`` (``parallel.p2p.FusedChannel``) make the first
+  GEMM wait on panel flags of the received activation, the last LayerNorm write into the next
+  stage's HBM, the first dgrad GEMM write its input-gradient tiles into the previous stage's HBM,
+  and the last LayerNorm-backward wait on the panels of the gradient it receives.
+
+Reference parity: the math is that of scaelum/model/bert_layers.py:171-395 (see the per-op
+citations in csrc/kernels/*.cu); tests/test_layers_gpu.py checks every span against the fp32
+PyTorch oracle in ``skycomputing_b200.models.bert_layers``.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence
+
+import torch
+
+from . import native as nat
+
+
+# --------------------------------------------------------------------------------------------
+# parameter bank: fp32 masters (possibly several nn.Parameters fused into one flat buffer) with a
+# bf16 shadow and a flat fp32 gradient buffer
+# --------------------------------------------------------------------------------------------
+class ParamBank:
+    """Fuses ``params`` (same trailing shape) along dim 0 into one flat fp32 master + grad buffer.
+
+    The original ``nn.Parameter`` objects keep their names/shapes (state_dict compatibility) but
+    become views into the flat storage; ``shadow()`` returns the bf16 compute copy, refreshed when
+    a master was modified through torch (version counter) - the fused optimizer refreshes it
+    itself in the same kernel that applies the update.
+    """
+
+    def __init__(self, params: Sequence[torch.nn.Parameter], need_shadow: bool = True):
+        self.params = list(params)
+        self.need_shadow = need_shadow
+        self.flat: Optional[torch.Tensor] = None
+        self.flat_grad: Optional[torch.Tensor] = None
+        self._shadow: Optional[torch.Tensor] = None
+        self._versions: List[int] = []
+        self._ptrs: List[int] = []
+
+    def _materialise(self) -> None:
+        p0 = self.params[0]
+        rows = sum(p.shape[0] for p in self.params)
+        shape = (rows,) + tuple(p0.shape[1:])
+        flat = torch.empty(shape, dtype=torch.float32, device=p0.device)
+        off = 0
+        with torch.no_grad():
+            for p in self.params:
+                n = p.shape[0]
+                flat[off:off + n].copy_(p.data.float())
+                p.data = flat[off:off + n]
+                off += n
+        self.flat = flat
+        self.flat_grad = torch.zeros_like(flat)
+        self._bind_grads()
+        self._ptrs = [p.data_ptr() for p in self.params]
+        self._shadow = None
+
+    def _bind_grads(self) -> None:
+        off = 0
+        for p in self.params:
+            n = p.shape[0]
+            p.grad = self.flat_grad[off:off + n]
+            off += n
+
+    def ensure(self) -> None:
+        if self.flat is None or any(p.data_ptr() != q for p, q in zip(self.params, self._ptrs)) \
+                or self.flat.device != self.params[0].device:
+            self._materialise()
+        elif any(p.grad is None or p.grad.data_ptr() < self.flat_grad.data_ptr()
+                 or p.grad.data_ptr() >= self.flat_grad.data_ptr() + self.flat_grad.numel() * 4
+                 for p in self.params):
+            # optimizer.zero_grad(set_to_none=True) or a foreign grad tensor: rebind (zeroed)
+            self.flat_grad.zero_()
+            self._bind_grads()
+
+    def master(self) -> torch.Tensor:
+        self.ensure()
+        return self.flat
+
+    def grad(self) -> torch.Tensor:
+        self.ensure()
+        return self.flat_grad
+
+    def shadow(self) -> torch.Tensor:
+        self.ensure()
+        versions = [p._version for p in self.params]
+        if self._shadow is None or versions != self._versions:
+            if self._shadow is None:
+                self._shadow = torch.empty(self.flat.shape, dtype=torch.bfloat16,
+                                           device=self.flat.device)
+            nat.cast_f32_to_bf16_(self.flat, self._shadow)
+            self._versions = versions
+        return self._shadow
+
+    def mark_shadow_fresh(self) -> None:
+        self._versions = [p._version for p in self.params]
+
+    def sgd_descriptor(self, momentum_buf: Optional[torch.Tensor] = None):
+        self.ensure()
+        if self.need_shadow and self._shadow is None:
+            self.shadow()
+        return (self.flat.data_ptr(), self.flat_grad.data_ptr(),
+                0 if momentum_buf is None else momentum_buf.data_ptr(),
+                self._shadow.data_ptr() if (self.need_shadow and self._shadow is not None) else 0,
+                self.flat.numel())
+
+
+class SpanParams:
+    """Parameter banks + hyper-parameters of one transformer-block span (any of Head/Body/Tail)."""
+
+    def __init__(self, head=None, body=None, tail=None):
+        self.has_head = head is not None
+        self.has_body = body is not None
+        self.has_tail = tail is not None
+        self.banks: List[ParamBank] = []
+        self.heads = 0
+        self.p_attn = 0.0
+        self.p_hidden = 0.0
+        self.eps = 1e-12
+        self.rng: Optional[nat.RngState] = None
+        self.rng_base = 0
+        if head is not None:
+            att = head.attention
+            self.heads = att.self.num_attention_heads
+            self.p_attn = float(att.self.dropout.p)
+            self.p_hidden = float(att.output.dropout.p)
+            self.eps = float(att.output.LayerNorm.eps)
+            self.wqkv = self._bank([att.self.query.weight, att.self.key.weight, att.self.value.weight])
+            self.bqkv = self._bank([att.self.query.bias, att.self.key.bias, att.self.value.bias], False)
+            self.wo = self._bank([att.output.dense.weight])
+            self.bo = self._bank([att.output.dense.bias], False)
+            self.g1 = self._bank([att.output.LayerNorm.weight], False)
+            self.b1n = self._bank([att.output.LayerNorm.bias], False)
+        if body is not None:
+            lin = body.intermediate.dense_act
+            self.w1 = self._bank([lin.weight])
+            self.b1 = self._bank([lin.bias], False)
+        if tail is not None:
+            out = tail.output
+            self.p_hidden = float(out.dropout.p)
+            self.eps = float(out.LayerNorm.eps)
+            self.w2 = self._bank([out.dense.weight])
+            self.b2 = self._bank([out.dense.bias], False)
+            self.g2 = self._bank([out.LayerNorm.weight], False)
+            self.b2n = self._bank([out.LayerNorm.bias], False)
+
+    def _bank(self, params, need_shadow: bool = True) -> ParamBank:
+        b = ParamBank(params, need_shadow)
+        self.banks.append(b)
+        return b
+
+    def all_params(self) -> List[torch.nn.Parameter]:
+        return [p for b in self.banks for p in b.params]
+
+
+def _flat2d(t: torch.Tensor) -> torch.Tensor:
+    return t.reshape(-1, t.shape[-1])
+
+
+def _ch_kwargs_wait(ch, mb: int) -> dict:
+    return dict(wait_flags=ch.act_flags_ptr(mb), wait_epoch=ch.epoch_ptr, wait_mult=ch.act_wait_mult,
+                error_flag=ch.error_ptr)
+
+
+class BertSpanFn(torch.autograd.Function):
+    """forward(ctx, sp, training, in_ch, out_ch, mb, n_in, *inputs_then_params)."""
+
+    @staticmethod
+    def forward(ctx, sp: SpanParams, training: bool, in_ch, out_ch, mb: int, n_in: int, *tensors):
+        inputs = tensors[:n_in]
+        rng = sp.rng
+        p_attn = sp.p_attn if training else 0.0
+        p_hid = sp.p_hidden if training else 0.0
+        if (p_attn > 0 or p_hid > 0) and rng is None:
+            raise RuntimeError("dropout requested but the span has no RngState attached")
+        saved = {}
+        if sp.has_head:
+            x3, mask = inputs[0], inputs[1]
+            B, S, H = x3.shape
+            x = _flat2d(x3)
+            mask2 = None if mask is None else mask.reshape(B, S)
+            wait = _ch_kwargs_wait(in_ch, mb) if in_ch is not None else {}
+            qkv = nat.gemm(x, sp.wqkv.shadow(), bias=sp.bqkv.master(), **wait)
+            ctxt, lse = nat.attention_fwd(qkv, mask2, B, S, sp.heads, dropout_p=p_attn, rng=rng,
+                                          rng_stream=sp.rng_base + 1)
+            z1 = nat.gemm(ctxt, sp.wo.shadow(), bias=sp.bo.master(), aux=x, add_aux=True,
+                          dropout_p=p_hid, rng=rng, rng_stream=sp.rng_base + 2)
+            ln_out = {}
+            if out_ch is not None and not sp.has_body:
+                ln_out = dict(y_ptr=out_ch.peer_act_ptr(mb), signal_flags=out_ch.peer_act_flags_ptr(mb))
+            y1, mean1, rstd1 = _ln_fwd(z1, sp.g1.master(), sp.b1n.master(), sp.eps, **ln_out)
+            saved.update(x=x, mask2=mask2, qkv=qkv, ctxt=ctxt, lse=lse, z1=z1, mean1=mean1,
+                         rstd1=rstd1)
+            a = y1
+            shape3 = (B, S, H)
+        else:
+            mask = inputs[-1]
+            if sp.has_body:
+                a3 = inputs[0]
+                B, S, H = a3.shape
+                a = _flat2d(a3)
+            else:
+                inter3, a3 = inputs[0], inputs[1]
+                B, S, H = a3.shape
+                a = _flat2d(a3)
+            shape3 = (B, S, H)
+        if sp.has_body:
+            wait = _ch_kwargs_wait(in_ch, mb) if (in_ch is not None and not sp.has_head) else {}
+            I = sp.w1.master().shape[0]
+            h1 = torch.empty((a.shape[0], I), dtype=torch.bfloat16, device=a.device)
+            inter = nat.gemm(a, sp.w1.shadow(), bias=sp.b1.master(), act=nat.ACT_GELU, out2=h1, **wait)
+            saved.update(h1=h1)
+        elif sp.has_tail:
+            inter = _flat2d(inputs[0])
+        if sp.has_tail:
+            wait = _ch_kwargs_wait(in_ch, mb) if (in_ch is not None and not sp.has_body) else {}
+            z2 = nat.gemm(inter, sp.w2.shadow(), bias=sp.b2.master(), aux=a, add_aux=True,
+                          dropout_p=p_hid, rng=rng, rng_stream=sp.rng_base + 3, **wait)
+            ln_out = {}
+            if out_ch is not None:
+                ln_out = dict(y_ptr=out_ch.peer_act_ptr(mb), signal_flags=out_ch.peer_act_flags_ptr(mb))
+            y2, mean2, rstd2 = _ln_fwd(z2, sp.g2.master(), sp.b2n.master(), sp.eps, **ln_out)
+            saved.update(z2=z2, mean2=mean2, rstd2=rstd2)
+        if sp.has_body or sp.has_tail:
+            saved.update(a=a, inter=inter)
+        ctx.sp, ctx.saved, ctx.training = sp, saved, training
+        ctx.in_ch, ctx.out_ch, ctx.mb, ctx.n_in = in_ch, out_ch, mb, n_in
+        ctx.n_tensors = len(tensors)
+        ctx.shape3 = shape3
+        B, S, H = shape3
+        if sp.has_tail:
+            out = y2.view(B, S, H) if y2 is not None else _dummy_out(a)
+            return out
+        if sp.has_body:
+            # the pass-through attention output is only returned when this span produced it;
+            # a span that starts at Body lets the caller forward its own input tensor
+            if sp.has_head:
+                return inter.view(B, S, -1), a.view(B, S, H)
+            return inter.view(B, S, -1)
+        return y1.view(B, S, H) if y1 is not None else _dummy_out(x)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        sp, sv = ctx.sp, ctx.saved
+        in_ch, out_ch, mb = ctx.in_ch, ctx.out_ch, ctx.mb
+        rng = sp.rng
+        p_attn = sp.p_attn if ctx.training else 0.0
+        p_hid = sp.p_hidden if ctx.training else 0.0
+        B, S, H = ctx.shape3
+        M = B * S
+        d_a_extra = None  # gradient flowing into `a` (attention output) besides the FFN1 dgrad
+        d_inter = None
+        g_in: List[Optional[torch.Tensor]] = [None] * ctx.n_in
+        if sp.has_tail:
+            wait = {}
+            if out_ch is not None:
+                dy2 = out_ch.grad_view(mb, M, H)
+                wait = dict(wait_flags=out_ch.grad_flags_ptr(mb), wait_epoch=out_ch.epoch_ptr,
+                            wait_mult=out_ch.grad_wait_mult, error_flag=out_ch.error_ptr)
+            else:
+                dy2 = _flat2d(grads[0]).contiguous()
+            dz2, dz2d = nat.layernorm_bwd(dy2, sv["z2"], sv["mean2"], sv["rstd2"], sp.g2.master(),
+                                          sp.g2.grad(), sp.b2n.grad(), dropout_p=p_hid, rng=rng,
+                                          rng_stream=sp.rng_base + 3, **wait)
+            g2 = dz2d if dz2d is not None else dz2
+            nat.gemm(g2, sv["inter"], a_mn=True, b_mn=True, out=sp.w2.grad(), accumulate=True)
+            nat.colsum_(g2, sp.b2.grad())
+            if sp.has_body:
+                d_h1 = nat.gemm(g2, sp.w2.shadow(), b_mn=True, aux=sv["h1"], act=nat.ACT_DGELU_MUL_AUX)
+            else:
+                send = _grad_send_kwargs(in_ch, mb, which=0)
+                d_inter = nat.gemm(g2, sp.w2.shadow(), b_mn=True, **send)
+            d_a_extra = dz2
+        elif sp.has_body:
+            # span ends after Body: grads = (d_inter, d_attn_out)
+            gi = _flat2d(grads[0]).contiguous()
+            d_h1 = torch.empty_like(gi)
+            nat.ext().dgelu_mul(gi.data_ptr(), sv["h1"].data_ptr(), d_h1.data_ptr(), gi.numel(),
+                                torch.cuda.current_stream().cuda_stream)
+            d_a_extra = None
+            if sp.has_head and len(grads) > 1 and grads[1] is not None:
+                d_a_extra = _flat2d(grads[1]).contiguous()
+        if sp.has_body:
+            nat.gemm(d_h1, sv["a"], a_mn=True, b_mn=True, out=sp.w1.grad(), accumulate=True)
+            nat.colsum_(d_h1, sp.b1.grad())
+            send = _grad_send_kwargs(in_ch, mb, which=0) if not sp.has_head else {}
+            d_a = nat.gemm(d_h1, sp.w1.shadow(), b_mn=True, aux=d_a_extra,
+                           add_aux=d_a_extra is not None, **send)
+        elif sp.has_tail:
+            d_a = d_a_extra  # tail-only span: grad of the attn_out input is dz2
+        else:
+            d_a = None
+        if sp.has_head:
+            wait = {}
+            if not sp.has_body:
+                if out_ch is not None:
+                    dy1 = out_ch.grad_view(mb, M, H)
+                    wait = dict(wait_flags=out_ch.grad_flags_ptr(mb), wait_epoch=out_ch.epoch_ptr,
+                                wait_mult=out_ch.grad_wait_mult, error_flag=out_ch.error_ptr)
+                else:
+                    dy1 = _flat2d(grads[0]).contiguous()
+            else:
+                dy1 = d_a
+            dz1, dz1d = nat.layernorm_bwd(dy1, sv["z1"], sv["mean1"], sv["rstd1"], sp.g1.master(),
+                                          sp.g1.grad(), sp.b1n.grad(), dropout_p=p_hid, rng=rng,
+                                          rng_stream=sp.rng_base + 2, **wait)
+            g1 = dz1d if dz1d is not None else dz1
+            nat.gemm(g1, sv["ctxt"], a_mn=True, b_mn=True, out=sp.wo.grad(), accumulate=True)
+            nat.colsum_(g1, sp.bo.grad())
+            dctx = nat.gemm(g1, sp.wo.shadow(), b_mn=True)
+            dqkv = nat.attention_bwd(sv["qkv"], sv["mask2"], sv["ctxt"], sv["lse"], dctx, B, S,
+                                     sp.heads, dropout_p=p_attn, rng=rng, rng_stream=sp.rng_base + 1)
+            nat.gemm(dqkv, sv["x"], a_mn=True, b_mn=True, out=sp.wqkv.grad(), accumulate=True)
+            nat.colsum_(dqkv, sp.bqkv.grad())
+            send = _grad_send_kwargs(in_ch, mb, which=0)
+            dx = nat.gemm(dqkv, sp.wqkv.shadow(), b_mn=True, aux=dz1, add_aux=True, **send)
+            g_in[0] = None if dx is None else dx.view(B, S, H)
+        elif sp.has_body:
+            g_in[0] = None if d_a is None else d_a.view(B, S, H)
+        else:  # tail only: inputs (inter, attn_out, mask)
+            g_in[0] = None if d_inter is None else d_inter.view(B, S, -1)
+            g_in[1] = d_a.view(B, S, H)
+        ctx.saved = None
+        return (None, None, None, None, None, None, *g_in, *([None] * (ctx.n_tensors - ctx.n_in)))
+
+
+def _dummy_out(like: torch.Tensor) -> torch.Tensor:
+    """Stand-in output for spans whose real output was written into the next stage's HBM."""
+    return torch.zeros(1, dtype=torch.bfloat16, device=like.device)
+
+
+def _ln_fwd(z, gamma, beta, eps, y_ptr: int = 0, signal_flags: int = 0):
+    M, H = z.shape
+    mean = torch.empty(M, dtype=torch.float32, device=z.device)
+    rstd = torch.empty(M, dtype=torch.float32, device=z.device)
+    if y_ptr:
+        y = None
+        yp = y_ptr
+    else:
+        y = torch.empty_like(z)
+        yp = y.data_ptr()
+    nat.ext().layernorm_fwd(z=z.data_ptr(), y=yp, mean=mean.data_ptr(), rstd=rstd.data_ptr(),
+                            gamma=gamma.data_ptr(), beta=beta.data_ptr(), M=M, H=H, eps=eps,
+                            signal_flags=signal_flags,
+                            stream=torch.cuda.current_stream().cuda_stream)
+    return y, mean, rstd
+
+
+def _grad_send_kwargs(in_ch, mb: int, which: int) -> dict:
+    """dgrad GEMM epilogue writes the input gradient straight into the previous stage's HBM."""
+    if in_ch is None:
+        return {}
+    return dict(out_ptr=in_ch.peer_grad_ptr(mb), out_ld=in_ch.grad_ld,
+                signal_flags=in_ch.peer_grad_flags_ptr(mb))
+
+
+# --------------------------------------------------------------------------------------------
+# embeddings / pooler / classifier / loss
+# --------------------------------------------------------------------------------------------
+class EmbeddingsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, emb, training: bool, out_ch, mb: int, input_ids, token_type_ids,
+                attention_mask, *params):
+        B, S = input_ids.shape
+        H = emb.word.master().shape[1]
+        dev = input_ids.device
+        ids = input_ids.reshape(-1).contiguous()
+        tts = token_type_ids.reshape(-1).contiguous()
+        am = attention_mask.reshape(-1).contiguous()
+        out = torch.empty((B * S, H), dtype=torch.bfloat16, device=dev)
+        ext_mask = torch.empty((B * S,), dtype=torch.float32, device=dev)
+        mean = torch.empty(B * S, dtype=torch.float32, device=dev)
+        rstd = torch.empty(B * S, dtype=torch.float32, device=dev)
+        p = emb.p_drop if training else 0.0
+        nat.ext().embed_fwd(ids=ids.data_ptr(), tts=tts.data_ptr(), amask=am.data_ptr(),
+                            word=emb.word.master().data_ptr(), pos=emb.pos.master().data_ptr(),
+                            type=emb.type.master().data_ptr(), gamma=emb.gamma.master().data_ptr(),
+                            beta=emb.beta.master().data_ptr(), out=out.data_ptr(),
+                            ext_mask=ext_mask.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr(),
+                            B=B, S=S, H=H, eps=emb.eps, dropout_p=p,
+                            rng_state=0 if emb.rng is None else emb.rng.ptr,
+                            rng_stream=emb.rng_base, stream=torch.cuda.current_stream().cuda_stream)
+        ctx.emb, ctx.training = emb, training
+        ctx.saved = (ids, tts, mean, rstd)
+        ctx.dims = (B, S, H)
+        ctx.n_params = len(params)
+        ctx.mark_non_differentiable(ext_mask)
+        return out.view(B, S, H), ext_mask.view(B, 1, 1, S)
+
+    @staticmethod
+    def backward(ctx, dout, _dmask):
+        emb = ctx.emb
+        ids, tts, mean, rstd = ctx.saved
+        B, S, H = ctx.dims
+        p = emb.p_drop if ctx.training else 0.0
+        dout = dout.reshape(B * S, H).contiguous()
+        nat.ext().embed_bwd(dout=dout.data_ptr(), ids=ids.data_ptr(), tts=tts.data_ptr(),
+                            word=emb.word.master().data_ptr(), pos=emb.pos.master().data_ptr(),
+                            type=emb.type.master().data_ptr(), gamma=emb.gamma.master().data_ptr(),
+                            mean=mean.data_ptr(), rstd=rstd.data_ptr(),
+                            dword=emb.word.grad().data_ptr(), dpos=emb.pos.grad().data_ptr(),
+                            dtype=emb.type.grad().data_ptr(), dgamma=emb.gamma.grad().data_ptr(),
+                            dbeta=emb.beta.grad().data_ptr(), B=B, S=S, H=H, dropout_p=p,
+                            rng_state=0 if emb.rng is None else emb.rng.ptr,
+                            rng_stream=emb.rng_base, stream=torch.cuda.current_stream().cuda_stream)
+        ctx.saved = None
+        return (None, None, None, None, None, None, None, *([None] * ctx.n_params))
+
+
+class EmbeddingParams:
+    def __init__(self, mod):
+        self.word = ParamBank([mod.word_embeddings.weight], False)
+        self.pos = ParamBank([mod.position_embeddings.weight], False)
+        self.type = ParamBank([mod.token_type_embeddings.weight], False)
+        self.gamma = ParamBank([mod.LayerNorm.weight], False)
+        self.beta = ParamBank([mod.LayerNorm.bias], False)
+        self.banks = [self.word, self.pos, self.type, self.gamma, self.beta]
+        self.eps = float(mod.LayerNorm.eps)
+        self.p_drop = float(mod.dropout.p)
+        self.rng: Optional[nat.RngState] = None
+        self.rng_base = 0
+
+    def all_params(self):
+        return [p for b in self.banks for p in b.params]
+
+
+class SmallLinearFn(torch.autograd.Function):
+    """Pooler (first-token gather + dense + tanh) and classifier (input dropout + dense)."""
+
+    @staticmethod
+    def forward(ctx, lp, training: bool, x, *params):
+        w, b = lp.w.master(), lp.b.master()
+        N, K = w.shape
+        if lp.first_token:
+            B, S, H = x.shape
+            M, ldx = B, S * H
+            xs = x.contiguous()
+        else:
+            xs = x.contiguous()
+            M, ldx = xs.shape[0], xs.shape[1]
+        x_bf16 = xs.dtype == torch.bfloat16
+        y = torch.empty((M, N), dtype=torch.float32, device=xs.device)
+        p = lp.p_drop if training else 0.0
+        nat.ext().small_linear_fwd(x=xs.data_ptr(), x_bf16=x_bf16, ldx=ldx, w=w.data_ptr(),
+                                   b=b.data_ptr(), y=y.data_ptr(), M=M, N=N, K=K,
+                                   act_tanh=1 if lp.act_tanh else 0, dropout_p=p,
+                                   rng_state=0 if lp.rng is None else lp.rng.ptr,
+                                   rng_stream=lp.rng_base, stream=torch.cuda.current_stream().cuda_stream)
+        ctx.lp, ctx.training = lp, training
+        ctx.saved = (xs, y, M, ldx, x_bf16)
+        ctx.n_params = len(params)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lp = ctx.lp
+        xs, y, M, ldx, x_bf16 = ctx.saved
+        w = lp.w.master()
+        N, K = w.shape
+        dy = dy.contiguous().float()
+        p = lp.p_drop if ctx.training else 0.0
+        if lp.first_token:
+            dx = torch.zeros_like(xs)
+            lddx = ldx
+        else:
+            dx = torch.empty_like(xs)
+            lddx = K
+        nat.ext().small_linear_bwd(x=xs.data_ptr(), x_bf16=x_bf16, ldx=ldx, w=w.data_ptr(),
+                                   y=y.data_ptr(), dy=dy.data_ptr(), dx=dx.data_ptr(),
+                                   dx_bf16=x_bf16, lddx=lddx, dw=lp.w.grad().data_ptr(),
+                                   db=lp.b.grad().data_ptr(), M=M, N=N, K=K,
+                                   act_tanh=1 if lp.act_tanh else 0, dropout_p=p,
+                                   rng_state=0 if lp.rng is None else lp.rng.ptr,
+                                   rng_stream=lp.rng_base, stream=torch.cuda.current_stream().cuda_stream)
+        ctx.saved = None
+        return (None, None, dx, *([None] * ctx.n_params))
+
+
+class SmallLinearParams:
+    def __init__(self, weight, bias, act_tanh: bool, first_token: bool, p_drop: float = 0.0):
+        self.w = ParamBank([weight], False)
+        self.b = ParamBank([bias], False)
+        self.banks = [self.w, self.b]
+        self.act_tanh = act_tanh
+        self.first_token = first_token
+        self.p_drop = p_drop
+        self.rng: Optional[nat.RngState] = None
+        self.rng_base = 0
+
+    def all_params(self):
+        return [p for b in self.banks for p in b.params]
+
+
+class SoftmaxCrossEntropyFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels):
+        loss, dlogits = nat.softmax_ce(logits.contiguous().float(), labels.contiguous())
+        ctx.save_for_backward(dlogits)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, dloss):
+        (dlogits,) = ctx.saved_tensors
+        return dlogits * dloss, None

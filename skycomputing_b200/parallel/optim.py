@@ -1,0 +1,138 @@
+"""Per-stage optimizers.
+
+``FusedSGD`` - one multi-tensor kernel launch per step over the stage's flat fp32 parameter banks:
+``p -= lr * (g/scale + wd * p)`` (optional momentum), refresh of the bf16 compute shadow and
+gradient zeroing in the same pass (csrc/kernels/elementwise_sm100.cu: sgd_multi_kernel).
+Parameters that do not live in a native bank (torch.nn fallback layers) are updated by a regular
+``torch.optim.SGD`` next to it.
+
+``build_optimizer`` keeps the reference's config contract (``optim_cfg = {optim_type: <any
+torch.optim class name>, **kwargs}``, experiment/launch.py:152-155): SGD on the native path maps
+to FusedSGD, everything else to the named ``torch.optim`` class over the fp32 masters (the bf16
+shadows are then refreshed lazily by version counter).  Optimizer state lives with the stage, as
+with the reference's DistributedOptimizer.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+
+class FusedSGD:
+    def __init__(self, module: nn.Module, lr: float = 1e-3, momentum: float = 0.0,
+                 weight_decay: float = 0.0, dampening: float = 0.0, nesterov: bool = False,
+                 banks: Optional[list] = None):
+        from ..models.bert_layers import native_param_banks
+        from ..ops import native as nat
+
+        if dampening != 0.0 or nesterov:
+            raise ValueError("FusedSGD supports plain / momentum SGD only")
+        self.lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self._nat = nat
+        self.banks = list(banks) if banks is not None else native_param_banks(module)
+        seen = set()
+        uniq = []
+        for b in self.banks:
+            if id(b) not in seen:
+                seen.add(id(b))
+                uniq.append(b)
+        self.banks = uniq
+        for b in self.banks:
+            b.ensure()
+        bank_params = {id(p) for b in self.banks for p in b.params}
+        rest = [p for p in module.parameters() if id(p) not in bank_params and p.requires_grad]
+        self._rest_opt = (torch.optim.SGD(rest, lr=lr, momentum=momentum, weight_decay=weight_decay)
+                          if rest else None)
+        self._mom = ([torch.zeros_like(b.master()) for b in self.banks] if momentum else
+                     [None] * len(self.banks))
+        self._desc_dev: Optional[torch.Tensor] = None
+        self._max_numel = 0
+        self.param_groups = [dict(lr=lr, momentum=momentum, weight_decay=weight_decay)]
+
+    def _descriptors(self) -> torch.Tensor:
+        if self._desc_dev is None and self.banks:
+            descs = [b.sgd_descriptor(m) for b, m in zip(self.banks, self._mom)]
+            raw = self._nat.ext().pack_sgd_descriptors(descs)
+            host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
+            self._desc_dev = host.to(self.banks[0].master().device)
+            self._max_numel = max(d[4] for d in descs)
+        return self._desc_dev
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        if self.banks:
+            d = self._descriptors()
+            self._nat.ext().sgd_multi(d_tensors=d.data_ptr(), n=len(self.banks),
+                                      max_numel=self._max_numel, lr=float(self.param_groups[0]["lr"]),
+                                      momentum=float(self.momentum),
+                                      weight_decay=float(self.weight_decay),
+                                      grad_scale=float(grad_scale), zero_grad=True,
+                                      stream=torch.cuda.current_stream().cuda_stream)
+        if self._rest_opt is not None:
+            self._rest_opt.step()
+            self._rest_opt.zero_grad(set_to_none=False)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        for b in self.banks:
+            b.grad().zero_()
+        if self._rest_opt is not None:
+            self._rest_opt.zero_grad(set_to_none=False)
+
+    def state_dict(self) -> dict:
+        return dict(momentum=[None if m is None else m.detach().cpu() for m in self._mom],
+                    rest=None if self._rest_opt is None else self._rest_opt.state_dict(),
+                    param_groups=self.param_groups)
+
+    def load_state_dict(self, sd: dict) -> None:
+        for m, s in zip(self._mom, sd.get("momentum", [])):
+            if m is not None and s is not None:
+                m.copy_(s)
+        if self._rest_opt is not None and sd.get("rest") is not None:
+            self._rest_opt.load_state_dict(sd["rest"])
+        self.param_groups = sd.get("param_groups", self.param_groups)
+
+
+class TorchOptimizerAdapter:
+    """Any ``torch.optim`` class over the stage's parameters; same step()/zero_grad() surface."""
+
+    def __init__(self, optimizer: torch.optim.Optimizer):
+        self.optimizer = optimizer
+        self.param_groups = optimizer.param_groups
+
+    def step(self, grad_scale: float = 1.0) -> None:
+        if grad_scale != 1.0:
+            for g in self.optimizer.param_groups:
+                for p in g["params"]:
+                    if p.grad is not None:
+                        p.grad.mul_(grad_scale)
+        self.optimizer.step()
+        self.optimizer.zero_grad(set_to_none=False)
+
+    def zero_grad(self, set_to_none: bool = False) -> None:
+        self.optimizer.zero_grad(set_to_none=False)
+
+    def state_dict(self):
+        return self.optimizer.state_dict()
+
+    def load_state_dict(self, sd):
+        self.optimizer.load_state_dict(sd)
+
+
+def build_optimizer(module: nn.Module, optim_cfg: dict, prefer_fused: bool = True):
+    cfg = dict(optim_cfg)
+    optim_type = cfg.pop("optim_type", "SGD")
+    params = [p for p in module.parameters() if p.requires_grad]
+    on_cuda = any(p.is_cuda for p in params)
+    if optim_type == "SGD" and prefer_fused and on_cuda:
+        from ..models.bert_layers import get_backend
+        from ..ops import native as nat
+
+        if get_backend() != "torch" and nat.available():
+            try:
+                return FusedSGD(module, **cfg)
+            except ValueError:
+                pass
+    if not params:
+        return TorchOptimizerAdapter(torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.0))
+    return TorchOptimizerAdapter(getattr(torch.optim, optim_type)(params, **cfg))

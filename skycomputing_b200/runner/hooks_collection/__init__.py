@@ -1,0 +1,5 @@
+from .checkpoint_hook import CheckpointHook
+from .distributed_timer_helper_hook import DistributedTimerHelperHook
+from .stop_hook import StopHook
+
+__all__ = ["CheckpointHook", "DistributedTimerHelperHook", "StopHook"]
