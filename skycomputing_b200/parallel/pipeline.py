@@ -85,7 +85,7 @@ class PipelineEngine:
         self._advance_rng = advance_rng
         self._pending_sends: list = []
         self.stage.engine_managed_backward = True
-        self.launches_last_step = 0
+        self.launches_per_step = 0
 
     # ------------------------------------------------------------------ setup
     def _native_active(self) -> bool:
@@ -337,9 +337,13 @@ class PipelineEngine:
             return self._loss_acc if self.is_last else None
         if self._graph is None:
             torch.cuda.synchronize(self.device)
+            from ..ops import native as nat
+
             g = torch.cuda.CUDAGraph()
+            before = nat.launch_count()
             with torch.cuda.graph(g):
                 self._step_body(self._static_inputs, self._static_labels)
+            self.launches_per_step = nat.launch_count() - before
             self._graph = g
             return self._loss_acc if self.is_last else None  # capture does not execute
         self._graph.replay()

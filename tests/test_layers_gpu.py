@@ -71,9 +71,13 @@ def _run_pair(layer_types, make_inputs, cfg, tol=4e-2, fused=True):
         torch.autograd.backward(outs_n, [c.to(o.dtype) for c, o in zip(cots, outs_n)])
     finally:
         set_backend("auto")
+    # key biases have a mathematically zero gradient (softmax shift invariance): compare against
+    # the overall gradient scale rather than each tensor's own (possibly ~0) magnitude
+    gmax = max(p.grad.abs().max().item() for p in ref.parameters())
     for (n, p_r), (_, p_n) in zip(ref.named_parameters(), nat.named_parameters()):
         assert p_n.grad is not None, f"no grad for {n}"
-        err = _max_rel(p_n.grad, p_r.grad)
+        scale = max(p_r.grad.abs().max().item(), 0.05 * gmax)
+        err = (p_n.grad.float() - p_r.grad.float()).abs().max().item() / scale
         assert err < tol, f"grad mismatch for {n}: {err}"
     for t_r, t_n in zip(ins_ref, ins_nat):
         if torch.is_tensor(t_r) and t_r.requires_grad:
