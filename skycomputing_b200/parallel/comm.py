@@ -74,16 +74,21 @@ class TorchDistComm:
         return self._meta_recv[key]
 
     # -- blocking-ish primitives --------------------------------------------------------------
-    def send(self, tensors: Sequence[Optional[torch.Tensor]], dst: int, direction: str) -> list:
-        self._send_meta(tensors, dst, (dst, direction))
+    def send(self, tensors: Sequence[Optional[torch.Tensor]], dst: int, direction: str,
+             with_meta: bool = True) -> list:
+        if with_meta:
+            self._send_meta(tensors, dst, (dst, direction))
         reqs = []
         for t in tensors:
             if t is not None:
                 reqs.append(dist.isend(t.contiguous(), dst, group=self.group))
         return reqs
 
-    def recv(self, src: int, direction: str) -> Tuple[list, list]:
-        metas = self._recv_meta(src, (src, direction))
+    def recv(self, src: int, direction: str, metas: Optional[list] = None) -> Tuple[list, list]:
+        """`metas` ([(dtype, shape) | None]) skips the metadata message (the caller knows the
+        layout, e.g. gradients mirror the tensors it sent)."""
+        if metas is None:
+            metas = self._recv_meta(src, (src, direction))
         outs, reqs = [], []
         for m in metas:
             if m is None:
@@ -95,10 +100,15 @@ class TorchDistComm:
             outs.append(buf)
         return outs, reqs
 
-    def exchange(self, send_tensors, dst: int, send_dir: str, src: int, recv_dir: str):
-        """Send to `dst` and receive from `src` as ONE batched p2p group (1F1B steady state)."""
-        self._send_meta(send_tensors, dst, (dst, send_dir))
-        metas = self._recv_meta(src, (src, recv_dir))
+    def exchange(self, send_tensors, dst: int, send_dir: str, src: int, recv_dir: str,
+                 recv_metas: list, send_with_meta: bool = False):
+        """Send to `dst` and receive from `src` as ONE batched p2p group (1F1B steady state).
+
+        The layout of what is received must be known (`recv_metas`): waiting for a metadata
+        message here would dead-lock, because the peer only answers after it got our payload."""
+        if send_with_meta:
+            self._send_meta(send_tensors, dst, (dst, send_dir))
+        metas = recv_metas
         ops, outs = [], []
         for t in send_tensors:
             if t is not None:
@@ -113,6 +123,9 @@ class TorchDistComm:
             outs.append(buf)
         reqs = dist.batch_isend_irecv(ops) if ops else []
         return outs, reqs
+
+    def cached_meta(self, src: int, direction: str) -> Optional[list]:
+        return self._meta_recv.get((src, direction))
 
     @staticmethod
     def wait(reqs) -> None:

@@ -221,44 +221,65 @@ class PipelineEngine:
         st.end_backward()
         if self.is_first or self.in_fused:
             return None
-        return [a.grad if (torch.is_tensor(a) and a.requires_grad) else None for a in args]
+        return self._in_grads(args)
 
     # ------------------------------------------------------------------ comm helpers (unfused)
+    @staticmethod
+    def _diff_flags(tensors) -> List[bool]:
+        """Which boundary tensors carry gradients: floating tensors, except a trailing additive
+        mask when several tensors cross the boundary.  Both sides of a link apply this rule, so
+        gradient messages need no metadata handshake."""
+        n = len(tensors)
+        return [torch.is_tensor(t) and t.is_floating_point() and (i < n - 1 or n == 1)
+                for i, t in enumerate(tensors)]
+
     def _recv_forward(self):
         outs, reqs = self.comm.recv(self.prev_rank, "fwd")
         self.comm.wait(reqs)
         return self._prep_inputs(outs)
 
     def _prep_inputs(self, tensors):
-        out = []
-        for i, t in enumerate(tensors):
-            # hidden states carry gradients; the additive mask (last tensor) does not
-            if t is not None and t.is_floating_point() and i < len(tensors) - 1 or \
-                    (t is not None and len(tensors) == 1 and t.is_floating_point()):
+        for t, d in zip(tensors, self._diff_flags(tensors)):
+            if d:
                 t.requires_grad_(True)
-            out.append(t)
-        return tuple(out)
+        return tuple(tensors)
+
+    def _grad_metas(self, outs):
+        return [(o.dtype, tuple(o.shape)) if d else None
+                for o, d in zip(outs, self._diff_flags(outs))]
+
+    def _in_grads(self, args):
+        out = []
+        for a, d in zip(args, self._diff_flags(args)):
+            if not d:
+                out.append(None)
+            else:
+                out.append(a.grad if a.grad is not None else torch.zeros_like(a))
+        return out
 
     def _send_forward(self, outs):
         self._pending_sends += self.comm.send([o.detach() if torch.is_tensor(o) else None
                                                for o in outs], self.next_rank, "fwd")
 
-    def _recv_backward(self):
-        outs, reqs = self.comm.recv(self.next_rank, "bwd")
+    def _recv_backward(self, outs):
+        grads, reqs = self.comm.recv(self.next_rank, "bwd", metas=self._grad_metas(outs))
         self.comm.wait(reqs)
-        return outs
+        return grads
 
     def _send_backward(self, in_grads):
-        self._pending_sends += self.comm.send(in_grads, self.prev_rank, "bwd")
+        self._pending_sends += self.comm.send(in_grads, self.prev_rank, "bwd", with_meta=False)
 
     def _send_forward_recv_backward(self, outs):
         g, reqs = self.comm.exchange([o.detach() if torch.is_tensor(o) else None for o in outs],
-                                     self.next_rank, "fwd", self.next_rank, "bwd")
+                                     self.next_rank, "fwd", self.next_rank, "bwd",
+                                     recv_metas=self._grad_metas(outs), send_with_meta=True)
         self.comm.wait(reqs)
         return g
 
     def _send_backward_recv_forward(self, in_grads):
-        x, reqs = self.comm.exchange(in_grads, self.prev_rank, "bwd", self.prev_rank, "fwd")
+        metas = self.comm.cached_meta(self.prev_rank, "fwd")
+        x, reqs = self.comm.exchange(in_grads, self.prev_rank, "bwd", self.prev_rank, "fwd",
+                                     recv_metas=metas)
         self.comm.wait(reqs)
         return self._prep_inputs(x)
 
@@ -300,7 +321,7 @@ class PipelineEngine:
                 args, outs, loss = saved.pop(j)
                 grads = None
                 if need_recv_b:
-                    grads = pending_grad if pending_grad is not None else self._recv_backward()
+                    grads = pending_grad if pending_grad is not None else self._recv_backward(outs)
                     pending_grad = None
                 in_grads = self._backward(j, outs, loss, grads, args)
                 if need_send_b:

@@ -32,7 +32,12 @@ def _dist():
 @HOOKS.register_module
 class CheckpointHook(Hook):
     def __init__(self, load_checkpoint_from: str = None, save_path: str = None,
-                 save_interval: int = None, save_optimizer: bool = True):
+                 save_interval: int = None, save_optimizer: bool = True,
+                 resume_training_state: bool = False):
+        # resume_training_state=True also restores optimizer state and the epoch / iteration
+        # counters from the per-rank ``.extra`` shards (same world size required); the default
+        # restores weights only, like the reference.
+        self._resume_training_state = resume_training_state
         self._load_checkpoint_from = load_checkpoint_from
         self._save_interval = save_interval
         self._save_path = save_path
@@ -55,7 +60,7 @@ class CheckpointHook(Hook):
         if runner.is_rank0:
             runner.parameter_server.load_weights_from_file(self._load_checkpoint_from)
         extra = self._extra_path(self._load_checkpoint_from, runner.rank)
-        if osp.exists(extra):
+        if self._resume_training_state and osp.exists(extra):
             st = torch.load(extra, map_location="cpu")
             if self._save_optimizer and st.get("optimizer") is not None:
                 try:

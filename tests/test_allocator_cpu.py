@@ -1,0 +1,201 @@
+"""Allocator parity + optimality (goldens: reference Allocator driven by fake benchmarkers,
+SURVEY Appendix A item 5; exact solver vs brute force; hypothesis invariants)."""
+import itertools
+
+import pytest
+from hypothesis import given, settings, strategies as st
+
+import skycomputing_b200 as sky
+from skycomputing_b200 import _core
+
+BIG = [1e9] * 8
+
+
+def entries(L):
+    return [0.0] + [36.507, 34.360, 34.360] * L + [0.067, 0.0]
+
+
+def counts(b):
+    return [b[i + 1] - b[i] for i in range(len(b) - 1)]
+
+
+GOLD_DYNAMIC = [
+    (24, [1] * 8, [10, 10, 10, 9, 9, 9, 9, 9], 352.2),
+    (24, [1, 1, 1, 2, 1, 1, 1, 1], [11, 10, 10, 8, 10, 10, 10, 6], 562.6),
+    (24, [2, 1, 1, 1, 1, 1, 1, 1], [10, 11, 11, 11, 11, 11, 9, 1], 631.4),
+    (24, [1, 1, 1, 1, 1, 1, 1, 2], [11, 10, 10, 10, 10, 10, 10, 4], 352.2),
+    (24, [1.0 + 0.2 * i for i in range(8)], [16, 12, 10, 9, 8, 7, 7, 6], 538.6),
+    (160, [1, 1, 1, 2, 1, 1, 1, 1], [68, 67, 66, 42, 67, 66, 66, 41], 2946.4),
+    (160, [2, 1, 1, 1, 1, 1, 1, 1], [61, 68, 68, 68, 68, 68, 68, 14], 4209.1),
+    (160, [1, 1, 1, 1, 1, 1, 1, 2], [68, 66, 66, 65, 64, 64, 64, 26], 2351.5),
+    (160, [1.0 + 0.2 * i for i in range(8)], [98, 79, 67, 59, 53, 47, 43, 37], 3403.8),
+]
+GOLD_EXACT = [
+    (24, [1] * 8, 315.7), (24, [1, 1, 1, 2, 1, 1, 1, 1], 352.2), (24, [2, 1, 1, 1, 1, 1, 1, 1], 352.2),
+    (24, [1, 1, 1, 1, 1, 1, 1, 2], 352.2), (24, [1.0 + 0.2 * i for i in range(8)], 506.4),
+    (160, [1] * 8, 2104.6), (160, [1, 1, 1, 2, 1, 1, 1, 1], 2246.3), (160, [2, 1, 1, 1, 1, 1, 1, 1], 2246.3),
+    (160, [1, 1, 1, 1, 1, 1, 1, 2], 2246.3), (160, [1.0 + 0.2 * i for i in range(8)], 3324.3),
+]
+
+
+def test_even_matches_reference():
+    assert counts(_core.even_partition(75, 8)) == [10, 10, 10, 9, 9, 9, 9, 9]
+    assert counts(_core.even_partition(483, 8)) == [61, 61, 61, 60, 60, 60, 60, 60]
+    assert counts(_core.even_partition(15, 1)) == [15]
+    assert counts(_core.even_partition(15, 2)) == [8, 7]
+
+
+@pytest.mark.parametrize("L,t,expect,bott", GOLD_DYNAMIC)
+def test_dynamic_compat_reproduces_reference(L, t, expect, bott):
+    lf = entries(L)
+    r = _core.dynamic_partition(lf, [1.0] * len(lf), t, BIG, compat=True)
+    assert counts(r["boundaries"]) == expect
+    assert r["bottleneck"] == pytest.approx(bott, abs=0.06)
+
+
+@pytest.mark.parametrize("L,t,bott", GOLD_EXACT)
+def test_exact_fixed_order_matches_bruteforce_goldens(L, t, bott):
+    lf = entries(L)
+    r = _core.optimal_partition(lf, [1.0] * len(lf), t, BIG, permute=False)
+    assert r["bottleneck"] == pytest.approx(bott, abs=0.06)
+    rp = _core.optimal_partition(lf, [1.0] * len(lf), t, BIG, permute=True)
+    assert rp["bottleneck"] <= r["bottleneck"] + 1e-9
+
+
+def test_memory_cap_cases():
+    lf = entries(24)
+    lm = [130.0] + [150.0, 260.0, 160.0] * 24 + [5.0, 1.0]
+    r = _core.dynamic_partition(lf, lm, [1] * 8, [1500.0] + [1e9] * 7, compat=True)
+    assert counts(r["boundaries"]) == [8, 12, 10, 9, 9, 9, 9, 9]
+    assert r["bottleneck"] == pytest.approx(420.9, abs=0.06)
+    with pytest.raises(RuntimeError, match="memory allocation failed"):
+        _core.dynamic_partition(lf, lm, [1] * 8, [100.0] * 8, compat=True)
+    with pytest.raises(RuntimeError, match="memory allocation failed"):
+        _core.optimal_partition(lf, lm, [1] * 8, [100.0] * 8)
+    # exact solver respects the cap
+    r = _core.optimal_partition(lf, lm, [1] * 8, [1500.0] + [1e9] * 7, permute=False)
+    b = r["boundaries"]
+    assert sum(lm[b[0]:b[1]]) <= 1500.0
+
+
+def _brute(lf, lm, dt, dm, permute):
+    L, D = len(lf), len(dt)
+    best = float("inf")
+    orders = itertools.permutations(range(D)) if permute else [tuple(range(D))]
+    for order in orders:
+        for cuts in itertools.combinations(range(1, L), D - 1):
+            b = (0,) + cuts + (L,)
+            ok, worst = True, 0.0
+            for k, d in enumerate(order):
+                if sum(lm[b[k]:b[k + 1]]) > dm[d]:
+                    ok = False
+                    break
+                worst = max(worst, dt[d] * sum(lf[b[k]:b[k + 1]]))
+            if ok:
+                best = min(best, worst)
+    return best
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(2, 4).flatmap(lambda D: st.tuples(
+    st.lists(st.floats(0.1, 10), min_size=D + 1, max_size=8),
+    st.lists(st.floats(0.5, 4), min_size=D, max_size=D),
+    st.booleans())))
+def test_exact_solver_equals_bruteforce(args):
+    lf, dt, permute = args
+    lm = [1.0] * len(lf)
+    dm = [1e9] * len(dt)
+    r = _core.optimal_partition(lf, lm, dt, dm, permute=permute)
+    assert r["bottleneck"] == pytest.approx(_brute(lf, lm, dt, dm, permute), rel=1e-6)
+    b = r["boundaries"]
+    assert b[0] == 0 and b[-1] == len(lf) and all(b[i] < b[i + 1] for i in range(len(b) - 1))
+    assert sorted(r["order"]) == list(range(len(dt)))
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.lists(st.floats(0.1, 10), min_size=8, max_size=40),
+       st.lists(st.floats(0.5, 4), min_size=2, max_size=6))
+def test_exact_le_heuristic_le_even(lf, dt):
+    if len(lf) < len(dt):
+        return
+    lm, dm = [1.0] * len(lf), [1e9] * len(dt)
+    even_b = _core.even_partition(len(lf), len(dt))
+    even = _core.partition_bottleneck(lf, lm, dt, dm, list(range(len(dt))), even_b)
+    heur = _core.dynamic_partition(lf, lm, dt, dm, compat=False)["bottleneck"]
+    exact = _core.optimal_partition(lf, lm, dt, dm, permute=False)["bottleneck"]
+    assert exact <= heur * (1 + 1e-9) <= even * (1 + 1e-9)
+
+
+class _FakeDev:
+    def __init__(self, times, mems):
+        self.t, self.m = times, mems
+
+    def benchmark(self):
+        return {f"worker{i}": dict(time=t, avai_mem=m) for i, (t, m) in enumerate(zip(self.t, self.m))}
+
+
+class _FakeModel:
+    def __init__(self, lf, lm):
+        self.lf, self.lm = lf, lm
+
+    def benchmark(self):
+        return self.lf, self.lm
+
+
+def _allocator(L, times, **kw):
+    lf = entries(L)
+    cfg = ([dict(layer_type="BertEmbeddings")] + [dict(layer_type="BertLayer_Head"),
+           dict(layer_type="BertLayer_Body"), dict(layer_type="BertLayer_Tail")] * L
+           + [dict(layer_type="BertPooler"), dict(layer_type="BertTailForClassification")])
+    wm = sky.WorkerManager(first_rank=0)
+    wm.load_worker_pool_from_config([dict(name=f"g{i}", server_config={}, extra_config={})
+                                     for i in range(len(times))])
+    return sky.Allocator(cfg, wm, _FakeModel(lf, [1.0] * len(lf)), _FakeDev(times, [1e9] * len(times)),
+                         **kw), cfg
+
+
+def test_allocator_front_end_assigns_contiguous_spans():
+    alloc, cfg = _allocator(24, [1] * 8)
+    wm = alloc.even_allocate()
+    assert [len(w.model_config) for w in wm.worker_pool] == [10, 10, 10, 9, 9, 9, 9, 9]
+    assert sum((w.model_config for w in wm.worker_pool), []) == cfg
+    alloc, cfg = _allocator(24, [2, 1, 1, 1, 1, 1, 1, 1], solver="compat")
+    wm = alloc.dynamic_allocate()
+    assert [len(w.model_config) for w in wm.worker_pool] == [10, 11, 11, 11, 11, 11, 9, 1]
+    alloc, cfg = _allocator(24, [2, 1, 1, 1, 1, 1, 1, 1])
+    wm = alloc.optimal_allocate()
+    assert alloc.last_result["bottleneck"] == pytest.approx(352.2, abs=0.06)
+    assert sum((w.model_config for w in wm.worker_pool), []) == cfg
+    assert [w.rank for w in wm.worker_pool] == list(range(8))
+    assert sorted(w.device for w in wm.worker_pool) == list(range(8))
+    spans = [w.layer_range for w in wm.worker_pool]
+    assert spans[0][0] == 0 and spans[-1][1] == len(cfg)
+    assert all(spans[i][1] == spans[i + 1][0] for i in range(7))
+
+
+def test_block_granularity_only_cuts_between_blocks():
+    alloc, cfg = _allocator(24, [1, 1, 1, 2, 1, 1, 1, 1], granularity="block")
+    for fn in (alloc.even_allocate, alloc.dynamic_allocate, alloc.optimal_allocate):
+        wm = fn()
+        for w in wm.worker_pool[:-1]:
+            end = w.layer_range[1]
+            assert cfg[end - 1]["layer_type"] in ("BertLayer_Tail", "BertEmbeddings", "BertPooler")
+        assert sum((w.model_config for w in wm.worker_pool), []) == cfg
+        # re-create the pool for the next strategy (allocation re-ranks it)
+        alloc, cfg = _allocator(24, [1, 1, 1, 2, 1, 1, 1, 1], granularity="block")
+
+
+def test_exact_solver_is_fast_for_paper_scale():
+    import time
+
+    lf = entries(160)
+    t0 = time.time()
+    r = _core.optimal_partition(lf, [1.0] * len(lf), [1, 1, 1, 2, 1, 1, 1, 1], BIG, permute=True)
+    assert time.time() - t0 < 1.0
+    assert r["bottleneck"] <= 2246.3 + 0.06
+    # 64 devices (the paper's cluster size): fixed-order DP + swap search
+    t = [1.0 + (i % 7) * 0.3 for i in range(64)]
+    r = _core.optimal_partition(lf, [1.0] * len(lf), t, [1e9] * 64, permute=True)
+    even = _core.partition_bottleneck(lf, [1.0] * len(lf), t, [1e9] * 64, list(range(64)),
+                                      _core.even_partition(len(lf), 64))
+    assert r["bottleneck"] < even
