@@ -366,7 +366,9 @@ class PipelineEngine:
                 self._step_body(self._static_inputs, self._static_labels)
             self.launches_per_step = nat.launch_count() - before
             self._graph = g
-            return self._loss_acc if self.is_last else None  # capture does not execute
+            # capture only records: replay right away so that this step's batch is trained on
+            self._graph.replay()
+            return self._loss_acc if self.is_last else None
         self._graph.replay()
         return self._loss_acc if self.is_last else None
 
