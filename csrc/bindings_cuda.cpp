@@ -199,8 +199,9 @@ void embed_bwd(uintptr_t dout, uintptr_t ids, uintptr_t tts, uintptr_t word, uin
                uintptr_t dpos, uintptr_t dtype_, uintptr_t dgamma, uintptr_t dbeta, int B, int Sq,
                int H, float dropout_p, uintptr_t rng_state, uint32_t rng_stream,
                uintptr_t wait_flags, uintptr_t wait_epoch, uint32_t wait_mult,
-               uintptr_t error_flag, uintptr_t stream) {
+               uintptr_t error_flag, int type_rows, uintptr_t stream) {
   sky::EmbedBwdArgs a;
+  a.type_rows = type_rows;
   a.dout = P<void>(dout);
   a.input_ids = P<const int64_t>(ids);
   a.token_type = P<const int64_t>(tts);
@@ -394,7 +395,7 @@ PYBIND11_MODULE(_cuda, m) {
         py::arg("B"), py::arg("S"), py::arg("H"), py::arg("dropout_p") = 0.f,
         py::arg("rng_state") = 0, py::arg("rng_stream") = 0, py::arg("wait_flags") = 0,
         py::arg("wait_epoch") = 0, py::arg("wait_mult") = 0, py::arg("error_flag") = 0,
-        py::arg("stream") = 0);
+        py::arg("type_rows") = 2, py::arg("stream") = 0);
   m.def("small_linear_fwd", &small_linear_fwd, py::arg("x"), py::arg("x_bf16"), py::arg("ldx"),
         py::arg("w"), py::arg("b"), py::arg("y"), py::arg("M"), py::arg("N"), py::arg("K"),
         py::arg("act_tanh") = 0, py::arg("dropout_p") = 0.f, py::arg("rng_state") = 0,

@@ -9,7 +9,7 @@ namespace sky {
 // ---------------------------------------------------------------------------------------------
 // GEMM  out[M,N] = epilogue( sum_k A[m,k] * B[n,k] )   bf16 operands, fp32 accumulation in TMEM
 // ---------------------------------------------------------------------------------------------
-enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_DGELU_MUL_AUX = 2 };
+enum GemmAct : int { ACT_NONE = 0, ACT_GELU = 1, ACT_DGELU_MUL_AUX = 2, ACT_TANH = 3 };
 
 struct GemmArgs {
   const void* A = nullptr;  // bf16
@@ -72,11 +72,11 @@ struct LayerNormFwdArgs {
   const uint32_t* wait_epoch = nullptr;
   uint32_t wait_mult = 0;
   int* error_flag = nullptr;
-  // optional: y is (peer) boundary memory; every CTA (32 rows) bumps signal_flags[row/128] once
-  // with release.sys, i.e. a 128-row panel is complete at 4 signals (kLnSignalsPerPanel)
+  // optional: y is (peer) boundary memory; every CTA (8 rows) bumps signal_flags[row/128] once
+  // with release.sys, i.e. a 128-row panel is complete at 16 signals (kLnSignalsPerPanel)
   uint32_t* signal_flags = nullptr;
 };
-constexpr int kLnSignalsPerPanel = 4;
+constexpr int kLnSignalsPerPanel = 16;
 int launch_layernorm_fwd(const LayerNormFwdArgs& a, cudaStream_t stream);
 
 struct LayerNormBwdArgs {
@@ -166,6 +166,7 @@ struct EmbedBwdArgs {
   float* dgamma = nullptr;
   float* dbeta = nullptr;
   int B = 0, S = 0, H = 0;
+  int type_rows = 2;  // rows of the token-type table (accumulated in shared memory when <= 4)
   float dropout_p = 0.f;
   const uint64_t* rng_state = nullptr;
   uint32_t rng_stream = 0;

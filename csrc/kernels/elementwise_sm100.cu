@@ -44,7 +44,7 @@ __device__ __forceinline__ void warp_wait_panel(const uint32_t* flags, int panel
 // H % 8 == 0, H <= 2048.  NV = number of 16B vectors per lane (compile-time).
 // ------------------------------------------------------------------------------------------
 constexpr int kLnMaxVec = 8;  // H <= 8*256
-constexpr int kLnRowsPerCta = 32;  // 128-row panel = 4 signals
+constexpr int kLnRowsPerCta = 8;  // one row per warp; a 128-row panel = 16 signals
 
 template <int NV>
 __global__ void __launch_bounds__(256)
@@ -413,7 +413,17 @@ embed_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const int64_t* __restri
                  float* __restrict__ dpos, float* __restrict__ dtype_, float* __restrict__ dgamma,
                  float* __restrict__ dbeta, int BS, int S, int H, float dropout_p,
                  const uint64_t* rng_state, uint32_t rng_stream, const uint32_t* wait_flags,
-                 const uint32_t* wait_epoch, uint32_t wait_mult, int* error_flag) {
+                 const uint32_t* wait_epoch, uint32_t wait_mult, int* error_flag,
+                 int type_rows_in_smem) {
+  // Heavily shared targets (LayerNorm gamma/beta: every row; token-type rows: ~half of all
+  // rows each) are accumulated in shared memory and flushed once per CTA; the first version
+  // issued one global atomic per element and spent 400 us serialising on ~4K addresses.
+  extern __shared__ float acc_smem[];  // [dgamma H][dbeta H][dtype type_rows_in_smem * H]
+  float* s_dgamma = acc_smem;
+  float* s_dbeta = acc_smem + H;
+  float* s_dtype = acc_smem + 2 * H;
+  for (int i = threadIdx.x; i < (2 + type_rows_in_smem) * H; i += blockDim.x) acc_smem[i] = 0.f;
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int row0 = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -469,8 +479,8 @@ embed_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const int64_t* __restri
         const float q = dy[t] * gm[t];
         s1 += q;
         s2 += q * xh;
-        atomicAdd(&dgamma[c + t], dy[t] * xh);
-        atomicAdd(&dbeta[c + t], dy[t]);
+        atomicAdd(&s_dgamma[c + t], dy[t] * xh);
+        atomicAdd(&s_dbeta[c + t], dy[t]);
       }
     }
     const float c1 = warp_sum(s1) * inv_h;
@@ -496,10 +506,20 @@ embed_bwd_kernel(const __nv_bfloat16* __restrict__ dout, const int64_t* __restri
         const float de = (dy[t] * gm[t] - c1 - xh * c2) * rs;
         atomicAdd(&dword[id * H + c + t], de);
         atomicAdd(&dpos[static_cast<long long>(s) * H + c + t], de);
-        atomicAdd(&dtype_[tt * H + c + t], de);
+        if (tt < type_rows_in_smem)
+          atomicAdd(&s_dtype[tt * H + c + t], de);
+        else
+          atomicAdd(&dtype_[tt * H + c + t], de);
       }
     }
   }
+  __syncthreads();
+  for (int i = threadIdx.x; i < H; i += blockDim.x) {
+    atomicAdd(&dgamma[i], s_dgamma[i]);
+    atomicAdd(&dbeta[i], s_dbeta[i]);
+  }
+  for (int i = threadIdx.x; i < type_rows_in_smem * H; i += blockDim.x)
+    atomicAdd(&dtype_[i], s_dtype[i]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -520,9 +540,11 @@ small_linear_fwd_kernel(const void* __restrict__ x, bool x_bf16, long long ldx,
                         const float* __restrict__ w, const float* __restrict__ b,
                         float* __restrict__ y, int M, int N, int K, int act_tanh, float dropout_p,
                         const uint64_t* rng_state, uint32_t rng_stream) {
+  // one warp per output element (m, n): lanes stride the reduction dimension
   const int lane = threadIdx.x & 31;
-  const int n = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (n >= N) return;
+  const long long o = static_cast<long long>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= static_cast<long long>(M) * N) return;
+  const int m = static_cast<int>(o / N), n = static_cast<int>(o % N);
   const bool has_dropout = dropout_p > 0.f;
   uint64_t seed = 0;
   uint32_t thr16 = 0;
@@ -533,30 +555,17 @@ small_linear_fwd_kernel(const void* __restrict__ x, bool x_bf16, long long ldx,
     scale = 1.f / (1.f - dropout_p);
   }
   const float* wr = w + static_cast<long long>(n) * K;
-  for (int m0 = 0; m0 < M; m0 += 8) {
-    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-    for (int k = lane; k < K; k += 32) {
-      const float wv = wr[k];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int m = m0 + i;
-        if (m < M) {
-          float xv = load_x(x, x_bf16, m * ldx + k);
-          if (has_dropout) xv = drop1(seed, static_cast<uint64_t>(m) * K + k, thr16, scale, xv);
-          acc[i] += xv * wv;
-        }
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float s = warp_sum(acc[i]);
-      const int m = m0 + i;
-      if (lane == 0 && m < M) {
-        float v = s + (b ? b[n] : 0.f);
-        if (act_tanh) v = tanhf(v);
-        y[static_cast<long long>(m) * N + n] = v;
-      }
-    }
+  float acc = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    float xv = load_x(x, x_bf16, m * ldx + k);
+    if (has_dropout) xv = drop1(seed, static_cast<uint64_t>(m) * K + k, thr16, scale, xv);
+    acc += xv * wr[k];
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) {
+    float v = acc + (b ? b[n] : 0.f);
+    if (act_tanh) v = tanhf(v);
+    y[o] = v;
   }
 }
 
@@ -919,12 +928,20 @@ int launch_embed_bwd(const EmbedBwdArgs& a, cudaStream_t stream) {
   const int BS = a.B * a.S;
   if (BS <= 0) return 0;
   if (a.H % 4 != 0) return 913;
-  const int grid = grid_for_rows(BS, 8, 148 * 8);
-  embed_bwd_kernel<<<grid, 256, 0, stream>>>(
+  const int grid = grid_for_rows(BS, 8, 148 * 2);
+  int t_smem = a.type_rows < 4 ? a.type_rows : 4;
+  if (t_smem < 0) t_smem = 0;
+  const size_t smem = static_cast<size_t>(2 + t_smem) * a.H * sizeof(float);
+  if (smem > 48 * 1024) {
+    t_smem = 0;
+  }
+  const size_t smem_used = static_cast<size_t>(2 + t_smem) * a.H * sizeof(float);
+  if (smem_used > 48 * 1024) return 915;
+  embed_bwd_kernel<<<grid, 256, smem_used, stream>>>(
       reinterpret_cast<const __nv_bfloat16*>(a.dout), a.input_ids, a.token_type, a.word, a.pos,
       a.type, a.gamma, a.mean, a.rstd, a.dword, a.dpos, a.dtype_, a.dgamma, a.dbeta, BS, a.S, a.H,
       a.dropout_p, a.rng_state, a.rng_stream, a.wait_flags, a.wait_epoch, a.wait_mult,
-      a.error_flag);
+      a.error_flag, t_smem);
   SKY_LAUNCH_CHECK();
 }
 
@@ -932,7 +949,8 @@ int launch_small_linear_fwd(const void* x, bool x_bf16, int ldx, const float* w,
                             float* y, int M, int N, int K, int act_tanh, float dropout_p,
                             const uint64_t* rng_state, uint32_t rng_stream, cudaStream_t stream) {
   if (M <= 0 || N <= 0) return 0;
-  const int grid = (N + 3) / 4;
+  const long long outs = static_cast<long long>(M) * N;
+  const int grid = static_cast<int>((outs + 3) / 4);
   small_linear_fwd_kernel<<<grid, 128, 0, stream>>>(x, x_bf16, ldx, w, b, y, M, N, K, act_tanh,
                                                     dropout_p, rng_state, rng_stream);
   SKY_LAUNCH_CHECK();

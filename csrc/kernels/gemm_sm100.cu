@@ -36,7 +36,7 @@ namespace {
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
-constexpr int kNumThreads = 256;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-7 epilogue
+constexpr int kNumThreads = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, warp3 idle, warps4-11 epilogue
 constexpr int kEpiWarp0 = 4;
 constexpr uint64_t kFlagTimeoutNs = 4000000000ull;  // 4 s
 
@@ -47,7 +47,9 @@ struct Cfg {
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 256 or 512 (power of two)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kBiasBytes = 2 * BLOCK_N * 4;  // double-buffered bias tile
+  static constexpr int kSmemBytes =
+      kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
 };
 
 struct GemmDev {
@@ -89,6 +91,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint64_t* tmem_full_bar = bars + 2 * kStages;    // [2]
   uint64_t* tmem_empty_bar = bars + 2 * kStages + 2;  // [2]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+  float* s_bias = reinterpret_cast<float*>(smem + kStages * C::kStageBytes + 256);
 
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -109,7 +112,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+      mbar_init(&tmem_empty_bar[i], 8);  // one arrive per epilogue warp
     }
     fence_barrier_init();
   }
@@ -204,9 +207,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     }
   } else if (warp_idx >= kEpiWarp0) {
     // ====================================== epilogue =======================================
-    const int q = warp_idx - kEpiWarp0;  // TMEM lane quadrant == warp_idx % 4
+    // 8 warps: warp e handles TMEM lane quadrant (e & 3) and column half (e >> 2) of the tile.
+    // Latency hiding (profiles/gemm_epilogue_v1.md: the first version stalled ~80% on
+    // long-scoreboard waits for bias/aux global loads with one warp per scheduler):
+    //   * bias for the tile is staged once in shared memory (double buffered per accumulator),
+    //   * aux (residual / pre-activation) chunks are prefetched one chunk ahead, the first one
+    //     before the accumulator is even ready,
+    //   * TMEM loads are double buffered: chunk c+1 is in flight while chunk c is processed,
+    //   * fp32 gradient accumulation uses red.global.add.v4.f32 (no read-modify-write).
+    const int e = warp_idx - kEpiWarp0;
+    const int q = e & 3;  // == warp_idx % 4: the TMEM lanes this warp may access
+    const int half = e >> 2;
+    constexpr int HALF_N = BLOCK_N / 2;
+    constexpr int NCH = HALF_N / 32;
+    const int epi_tid = threadIdx.x - kEpiWarp0 * 32;  // 0..255
     const int row_in_tile = q * 32 + lane;
     const bool has_dropout = p.dropout_p > 0.f;
+    const bool has_aux = p.aux != nullptr;
     uint64_t seed = 0;
     uint32_t thr16 = 0;
     float drop_scale = 1.f;
@@ -221,32 +238,46 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_blk = tile / num_m_blks;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      mbar_wait(&tmem_full_bar[acc], acc_phase);
-      tcgen05_fence_after();
       const long long row = static_cast<long long>(m_blk) * BLOCK_M + row_in_tile;
       const bool row_ok = row < p.M;
-      const uint32_t taddr_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N;
-#pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr_row + c * 32, v);
-        tmem_ld_wait();
-        const int col0 = n_blk * BLOCK_N + c * 32;
-        if (col0 >= p.N) continue;  // warp-uniform
+      const int colbase = n_blk * BLOCK_N + half * HALF_N;
+      // ---- stage bias, prefetch first aux chunk (both overlap the MMA main loop) ----
+      float* sb = s_bias + acc * BLOCK_N;
+      if (epi_tid < BLOCK_N) {
+        const int gc = n_blk * BLOCK_N + epi_tid;
+        sb[epi_tid] = (p.bias != nullptr && gc < p.N) ? __ldg(p.bias + gc) : 0.f;
+      }
+      uint4 auxa[4], auxb[4];
+      const __nv_bfloat16* aux_row = has_aux ? p.aux + row * p.ldaux + colbase : nullptr;
+      auto load_aux = [&](uint4 (&dst)[4], int c) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const int col = colbase + c * 32 + t * 8;
+          dst[t] = (has_aux && row_ok && col < p.N)
+                       ? *reinterpret_cast<const uint4*>(aux_row + c * 32 + t * 8)
+                       : make_uint4(0, 0, 0, 0);
+        }
+      };
+      if (has_aux) load_aux(auxa, 0);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // bias of this tile visible to all 8 warps
+
+      mbar_wait(&tmem_full_bar[acc], acc_phase);
+      tcgen05_fence_after();
+      const uint32_t taddr =
+          tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * HALF_N;
+
+      auto process = [&](uint32_t (&v)[32], uint4 (&ax)[4], int c) {
+        const int col0 = colbase + c * 32;
+        if (col0 >= p.N) return;  // warp-uniform
         float f[32];
+        const float4* sb4 = reinterpret_cast<const float4*>(sb + half * HALF_N + c * 32);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            if (col0 + j < p.N) {
-              const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-              f[j] += b.x;
-              f[j + 1] += b.y;
-              f[j + 2] += b.z;
-              f[j + 3] += b.w;
-            }
-          }
+        for (int j = 0; j < 32; j += 4) {
+          const float4 bb = sb4[j >> 2];  // smem broadcast
+          f[j] = __uint_as_float(v[j]) + bb.x;
+          f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+          f[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
+          f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
         }
         if (p.act == ACT_GELU) {
           if (p.out2 != nullptr && row_ok) {
@@ -264,7 +295,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+          for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+        } else if (p.act == ACT_TANH) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = tanh_fast(f[j]);
         }
         if (has_dropout) {
 #pragma unroll
@@ -277,23 +311,20 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             f[j + 3] = (m & 8u) ? f[j + 3] * drop_scale : 0.f;
           }
         }
-        if (p.aux != nullptr && row_ok) {
-          const __nv_bfloat16* ax = p.aux + row * p.ldaux + col0;
+        if (has_aux) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            if (col0 + j < p.N) {
-              const uint4 a = *reinterpret_cast<const uint4*>(ax + j);
-              const uint32_t aw[4] = {a.x, a.y, a.z, a.w};
+          for (int t = 0; t < 4; ++t) {
+            const uint32_t aw[4] = {ax[t].x, ax[t].y, ax[t].z, ax[t].w};
 #pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 x = unpack_bf16x2(aw[t]);
-                if (p.act == ACT_DGELU_MUL_AUX) {
-                  f[j + 2 * t] *= dgelu_erf(x.x);
-                  f[j + 2 * t + 1] *= dgelu_erf(x.y);
-                } else if (p.add_aux) {
-                  f[j + 2 * t] += x.x;
-                  f[j + 2 * t + 1] += x.y;
-                }
+            for (int u = 0; u < 4; ++u) {
+              const float2 x = unpack_bf16x2(aw[u]);
+              const int j = t * 8 + u * 2;
+              if (p.act == ACT_DGELU_MUL_AUX) {
+                f[j] *= dgelu_fast(x.x);
+                f[j + 1] *= dgelu_fast(x.y);
+              } else if (p.add_aux) {
+                f[j] += x.x;
+                f[j + 1] += x.y;
               }
             }
           }
@@ -304,15 +335,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               if (col0 + j < p.N) {
-                float4 r = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-                if (p.accumulate) {
-                  const float4 old = *reinterpret_cast<const float4*>(o + j);
-                  r.x += old.x;
-                  r.y += old.y;
-                  r.z += old.z;
-                  r.w += old.w;
-                }
-                *reinterpret_cast<float4*>(o + j) = r;
+                if (p.accumulate)
+                  red_add_v4_f32(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+                else
+                  *reinterpret_cast<float4*>(o + j) =
+                      make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
               }
             }
           } else {
@@ -330,16 +357,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         }
+      };
+
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        tmem_ld_wait();                                // chunk c landed in va
+        tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);  // chunk c+1 in flight
+        if (has_aux) load_aux(auxb, c + 1);
+        process(va, auxa, c);
+        tmem_ld_wait();  // chunk c+1 landed in vb
+        if (c + 2 < NCH) {
+          tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
+          if (has_aux) load_aux(auxa, c + 2);
+        }
+        process(vb, auxb, c + 1);
       }
       // release the TMEM buffer back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       if (p.signal_flags != nullptr) {
-        // publish this tile: all 128 epilogue threads' stores -> barrier -> one release.sys
+        // publish this tile: all 256 epilogue threads' stores -> barrier -> one release.sys
         __threadfence_system();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (threadIdx.x == kEpiWarp0 * 32) red_release_sys_add(p.signal_flags + m_blk, 1u);
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (epi_tid == 0) red_release_sys_add(p.signal_flags + m_blk, 1u);
       }
     }
   }

@@ -414,9 +414,12 @@ class BertPooler(nn.Module):
 
     def forward(self, hidden_states, attention_mask):
         if _native_enabled(hidden_states) and hidden_states.dim() == 3:
-            from ..ops.functions import SmallLinearFn
+            from ..ops.functions import PoolerFn, SmallLinearFn
 
             lp = self._native_params()
+            B, _S, H = hidden_states.shape
+            if B % 8 == 0 and H % 8 == 0 and hidden_states.dtype == torch.bfloat16:
+                return PoolerFn.apply(lp, hidden_states, *lp.all_params())  # tcgen05 GEMM path
             return SmallLinearFn.apply(lp, self.training, hidden_states, *lp.all_params())
         first_token_tensor = hidden_states[:, 0].float()
         return self.dense_act(first_token_tensor)

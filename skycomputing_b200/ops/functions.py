@@ -416,7 +416,8 @@ class EmbeddingsFn(torch.autograd.Function):
                             mean=mean.data_ptr(), rstd=rstd.data_ptr(),
                             dword=emb.word.grad().data_ptr(), dpos=emb.pos.grad().data_ptr(),
                             dtype=emb.type.grad().data_ptr(), dgamma=emb.gamma.grad().data_ptr(),
-                            dbeta=emb.beta.grad().data_ptr(), B=B, S=S, H=H, dropout_p=p,
+                            dbeta=emb.beta.grad().data_ptr(), B=B, S=S, H=H,
+                            type_rows=emb.type.master().shape[0], dropout_p=p,
                             rng_state=0 if emb.rng is None else emb.rng.ptr,
                             rng_stream=emb.rng_base, stream=torch.cuda.current_stream().cuda_stream)
         ctx.saved = None
@@ -492,9 +493,46 @@ class SmallLinearFn(torch.autograd.Function):
         return (None, None, dx, *([None] * ctx.n_params))
 
 
+class PoolerFn(torch.autograd.Function):
+    """BertPooler on the tensor-core GEMM: first-token rows are read through a strided TMA view
+    (no gather copy), bias + tanh run in the epilogue; backward = two more GEMMs.
+
+    Reference: scaelum/model/bert_layers.py:381-395.
+    """
+
+    @staticmethod
+    def forward(ctx, lp, hidden, *params):
+        B, S, H = hidden.shape
+        hidden = hidden.contiguous()
+        x0 = hidden.view(B, S * H)[:, :H]          # [B, H] view, row stride S*H
+        y = nat.gemm(x0, lp.w.shadow(), bias=lp.b.master(), act=nat.ACT_TANH,
+                     out_dtype=torch.float32)
+        ctx.lp = lp
+        ctx.saved = (hidden, y)
+        ctx.n_params = len(params)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lp = ctx.lp
+        hidden, y = ctx.saved
+        B, S, H = hidden.shape
+        x0 = hidden.view(B, S * H)[:, :H]
+        g = (dy.float() * (1.0 - y * y))
+        lp.b.grad().add_(g.sum(0))
+        gb = g.to(torch.bfloat16)
+        # dW[n,k] += sum_b g[b,n] x0[b,k]  (both operands MN-major over the batch dimension)
+        nat.gemm(gb, x0, a_mn=True, b_mn=True, out=lp.w.grad(), accumulate=True)
+        dhidden = torch.zeros_like(hidden)
+        nat.gemm(gb, lp.w.shadow(), b_mn=True, out=dhidden.view(B, S * H)[:, :H])
+        ctx.saved = None
+        return (None, dhidden, *([None] * ctx.n_params))
+
+
 class SmallLinearParams:
     def __init__(self, weight, bias, act_tanh: bool, first_token: bool, p_drop: float = 0.0):
-        self.w = ParamBank([weight], False)
+        # the pooler (first_token) also runs on the GEMM kernel -> keep a bf16 shadow of its weight
+        self.w = ParamBank([weight], need_shadow=first_token)
         self.b = ParamBank([bias], False)
         self.banks = [self.w, self.b]
         self.act_tanh = act_tanh

@@ -24,7 +24,7 @@ try:  # the .so is built in-tree by skycomputing_b200._build / __graft_entry__.b
 except Exception as e:  # pragma: no cover - exercised only when the build is missing
     _import_error = e
 
-ACT_NONE, ACT_GELU, ACT_DGELU_MUL_AUX = 0, 1, 2
+ACT_NONE, ACT_GELU, ACT_DGELU_MUL_AUX, ACT_TANH = 0, 1, 2, 3
 
 
 def available() -> bool:
