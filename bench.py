@@ -40,7 +40,10 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
-    ap.add_argument("--alloc", type=str, default="even", choices=["even", "dynamic", "optimal"])
+    # `optimal` = the framework's exact load-balancing allocator over device benchmarks (the
+    # capability under test); `even` is the reference's baseline split for comparison
+    ap.add_argument("--alloc", type=str, default=os.environ.get("SKY_ALLOC", "optimal"),
+                    choices=["even", "dynamic", "optimal"])
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("SKY_MICRO_BATCH", "0")),
                     help="sequences per micro-batch (0 = auto)")
     ap.add_argument("--boundary", type=str, default=os.environ.get("SKY_BOUNDARY", "auto"))
@@ -151,7 +154,7 @@ def run_ours(args) -> dict:
         gen = sky.build_data_generator("DataloaderGenerator", generator_cfg=dict(
             dataset_cfg=dict(type="SynthMNLIDataset", num_samples=mb, max_seq_length=SEQ_LEN),
             dataloader_cfg=dict(batch_size=mb)))
-        model_bench = sky.ModelBenchmarker(model_config, gen, device="cpu")
+        model_bench = sky.ModelBenchmarker(model_config, gen, device="cpu", analytic=True)
         dev_bench = sky.DeviceBenchmarker(wm, None, model_config=[], iterations=20, warmup=3,
                                           proxy="bert_block",
                                           block_shape=dict(tokens=mb * SEQ_LEN, hidden=1024,

@@ -70,6 +70,61 @@ class Estimator:
         return output, flops, mem_usage
 
     @staticmethod
+    def analytic_layer_cost(layer_cfg: dict, data, param_scale: int = 2):
+        """Closed-form (flops, mem_MiB, output_meta) for the registered BERT layers, or None.
+
+        FLOPs follow FlopCounterMode's convention (2 per multiply-accumulate of every matmul);
+        memory follows the reference formula (2 x forward-hook outputs + param_scale x params +
+        inputs, 4 bytes each).  tests/test_core_cpu.py checks both against the measured path.
+        """
+        lt = layer_cfg.get("layer_type")
+        data = data if isinstance(data, (list, tuple)) else (data,)
+        c = layer_cfg.get("config")
+        mb = 1024.0 ** 2
+        f32 = torch.float32
+        if lt == "BertTailForClassification":
+            B, H = data[0].shape
+            C = layer_cfg["num_classes"]
+            params = H * C + C
+            outs = B * H + 2 * B * C      # dropout, linear, the layer module itself
+            mem = (2 * outs + param_scale * params + B * H) * 4 / mb
+            return 2.0 * B * H * C, mem, [((B, C), f32)]
+        if c is None or lt not in ("BertEmbeddings", "BertLayer_Head", "BertLayer_Body",
+                                   "BertLayer_Tail", "BertPooler"):
+            return None
+        H, I, A = c["hidden_size"], c["intermediate_size"], c["num_attention_heads"]
+        if lt == "BertEmbeddings":
+            B, S = data[0].shape
+            params = (c["vocab_size"] + c["max_position_embeddings"] + c["type_vocab_size"]) * H + 2 * H
+            outs = 6 * B * S * H + B * S  # 3 lookups, LayerNorm, dropout, the module's own tuple
+            mem = (2 * outs + param_scale * params + 3 * B * S) * 4 / mb
+            return 0.0, mem, [((B, S, H), f32), ((B, 1, 1, S), f32)]
+        if lt == "BertPooler":
+            B, S, _ = data[0].shape
+            params = H * H + H
+            mem = (2 * 2 * B * H + param_scale * params + B * S * H + B * S) * 4 / mb
+            return 2.0 * B * H * H, mem, [((B, H), f32)]
+        if lt == "BertLayer_Head":
+            B, S, _ = data[0].shape
+            flops = 4 * 2.0 * B * S * H * H + 2 * 2.0 * B * S * S * H
+            params = 4 * (H * H + H) + 2 * H
+            outs = 10 * B * S * H + B * A * S * S + B * S   # every sub-module output is hooked
+            mem = (2 * outs + param_scale * params + B * S * H + B * S) * 4 / mb
+            return flops, mem, [((B, S, H), f32), ((B, 1, 1, S), f32)]
+        if lt == "BertLayer_Body":
+            B, S, _ = data[0].shape
+            params = H * I + I
+            outs = 3 * B * S * I + B * S * H + B * S
+            mem = (2 * outs + param_scale * params + B * S * H + B * S) * 4 / mb
+            return 2.0 * B * S * H * I, mem, [((B, S, I), f32), ((B, S, H), f32), ((B, 1, 1, S), f32)]
+        # BertLayer_Tail
+        B, S, _ = data[1].shape
+        params = I * H + H + 2 * H
+        outs = 5 * B * S * H + B * S
+        mem = (2 * outs + param_scale * params + B * S * I + B * S * H + B * S) * 4 / mb
+        return 2.0 * B * S * I * H, mem, [((B, S, H), f32), ((B, 1, 1, S), f32)]
+
+    @staticmethod
     def _calc_flops(model, data) -> float:
         data = tuple(d.detach() if torch.is_tensor(d) else d for d in data)
         with FlopCounterMode(display=False) as fc:

@@ -211,6 +211,17 @@ def test_model_benchmarker_generic_dedup():
     assert all(m > 0 for m in mem)
 
 
+def test_analytic_model_benchmark_matches_measured():
+    cfg = _tiny_bert_cfg(2)
+    gen = sky.build_data_generator("DataloaderGenerator", generator_cfg=dict(
+        dataset_cfg=dict(type="SynthMNLIDataset", num_samples=4, max_seq_length=16, vocab_size=100),
+        dataloader_cfg=dict(batch_size=4)))
+    f_meas, m_meas = sky.ModelBenchmarker(cfg, gen, device="cpu").benchmark()
+    f_ana, m_ana = sky.ModelBenchmarker(cfg, gen, device="cpu", analytic=True).benchmark()
+    assert f_ana == pytest.approx(f_meas, rel=1e-6, abs=1e-6)
+    assert m_ana == pytest.approx(m_meas, rel=0.05)
+
+
 def test_device_benchmarker_single_process_with_slowdown_and_stimulate(monkeypatch):
     wm = sky.WorkerManager()
     wm.load_worker_pool_from_config([
