@@ -47,6 +47,7 @@ struct GemmArgs {
   uint32_t wait_mult = 0;
   int* error_flag = nullptr;  // set to non-zero on flag-wait timeout
   int block_n = 0;            // 0 = auto (128 or 256)
+  int debug = 0;              // perf triage: 1 = epilogue discards the tile, 2 = epilogue math but no stores
   int max_ctas = 0;           // 0 = all SMs
 };
 

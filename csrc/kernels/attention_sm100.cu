@@ -213,22 +213,25 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnDev
 // ----------------------------------------------------------------------------------------------
 // backward
 // ----------------------------------------------------------------------------------------------
-constexpr int kBwdSmem = 4 * kTile + 4 * kTile /*P, dS*/ + 1024 + 512 + 64;
+// 7 tiles (Q, K, V, dO, P1, dS0, dS1; P0 re-uses V once dP = dO V^T has retired) + mask + barriers:
+// 115,264 B, i.e. two CTAs fit one SM (the 1024-B alignment comes from the declaration, no slack).
+constexpr int kBwdSmem = 7 * kTile + 512 + 64;
 
-__global__ void __launch_bounds__(128, 1)
+__global__ void __launch_bounds__(128, 2)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
                      const __grid_constant__ CUtensorMap tmap_do, const AttnDev p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
-                                             ~static_cast<uintptr_t>(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw;
+  if ((smem_u32(smem) & 1023u) != 0) __trap();  // SWIZZLE_128B tiles need 1024-B alignment
   uint8_t* sQ = smem;
   uint8_t* sK = smem + kTile;
   uint8_t* sV = smem + 2 * kTile;
   uint8_t* sdO = smem + 3 * kTile;
-  uint8_t* sP = smem + 4 * kTile;   // 2 blocks
-  uint8_t* sdS = smem + 6 * kTile;  // 2 blocks
-  float* sMask = reinterpret_cast<float*>(smem + 8 * kTile);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 8 * kTile + 512);
+  uint8_t* sP0 = sV;                // keys 0..63 of P: V is dead once dP has been computed
+  uint8_t* sP1 = smem + 4 * kTile;  // keys 64..127 of P
+  uint8_t* sdS = smem + 5 * kTile;  // 2 blocks
+  float* sMask = reinterpret_cast<float*>(smem + 7 * kTile);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 7 * kTile + 512);
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x;
@@ -246,7 +249,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     fence_barrier_init();
   }
   if (warp == 0) {
-    tmem_alloc(tmem_ptr_smem, 512);
+    tmem_alloc(tmem_ptr_smem, 256);
     tmem_relinquish();
   }
   sMask[tid] = p.mask ? p.mask[b * kS + tid] * kLog2e : 0.f;
@@ -254,7 +257,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
-  constexpr uint32_t cS = 0, cdP = 128, cdV = 256, cdK = 320, cdQ = 384;
+  // S and dP are dead after the softmax phase: the three output accumulators re-use their columns
+  constexpr uint32_t cS = 0, cdP = 128, cdV = 0, cdK = 64, cdQ = 128;
 
   if (tid == 0) {
     mbar_expect_tx(&bars[0], 4 * kTile);
@@ -346,7 +350,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
 #pragma unroll
       for (int j = 0; j < 16; ++j) ds[j] = pd[j] * (ds[j] - delta) * p.scale;
     }
-    uint8_t* bp = sP + (c >> 2) * kTile;
+    uint8_t* bp = (c >> 2) ? sP1 : sP0;
     uint8_t* bd = sdS + (c >> 2) * kTile;
 #pragma unroll
     for (int j = 0; j < 16; j += 8) {
@@ -375,7 +379,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     constexpr uint32_t idesc_t = make_idesc_bf16_f32(128, 64, true, true);
 #pragma unroll
     for (int j = 0; j < kS / 16; ++j) {
-      const uint64_t da = make_smem_desc_sw128(smem_u32(sP) + j * 2048, kTile, 1024);
+      const uint64_t da = make_smem_desc_sw128(smem_u32(sP0) + j * 2048, 2 * kTile, 1024);
       const uint64_t db = make_smem_desc_sw128(smem_u32(sdO) + j * 2048, kTile, 1024);
       umma_bf16_ss(tmem_base + cdV, da, db, idesc_t, j);
     }
@@ -424,7 +428,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   __syncthreads();
   if (warp == 0) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 512);
+    tmem_dealloc(tmem_base, 256);
   }
 }
 

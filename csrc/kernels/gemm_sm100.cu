@@ -48,8 +48,9 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 256 or 512 (power of two)
   static constexpr int kBiasBytes = 2 * BLOCK_N * 4;  // double-buffered bias tile
-  static constexpr int kSmemBytes =
-      kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + kBiasBytes;
+  static constexpr int kOutStageBytes = 8 * 32 * 80;  // per epilogue warp: 32 rows x (64+16) B
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ +
+                                    256 /*barriers*/ + kBiasBytes + kOutStageBytes;
 };
 
 struct GemmDev {
@@ -70,6 +71,7 @@ struct GemmDev {
   const uint32_t* wait_epoch;
   uint32_t wait_mult;
   int* error_flag;
+  int debug;
 };
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32>
@@ -221,6 +223,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     constexpr int HALF_N = BLOCK_N / 2;
     constexpr int NCH = HALF_N / 32;
     const int epi_tid = threadIdx.x - kEpiWarp0 * 32;  // 0..255
+    uint8_t* s_stage = smem + kStages * C::kStageBytes + 256 + C::kBiasBytes + e * (32 * 80);
     const int row_in_tile = q * 32 + lane;
     const bool has_dropout = p.dropout_p > 0.f;
     const bool has_aux = p.aux != nullptr;
@@ -266,9 +269,42 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * HALF_N;
 
+      // bf16 stores go through a per-warp smem transpose: a lane owns one accumulator ROW, so
+      // storing straight from registers makes every STG.128 touch 32 different rows (32 partial
+      // sectors per request).  Staged, a warp store covers 8 rows x 64 contiguous bytes.
+      // Row stride 80 B keeps both the row-wise writes and the 4-lanes-per-row reads (nearly)
+      // bank-conflict free.
+      const long long warp_row0 = static_cast<long long>(m_blk) * BLOCK_M + q * 32;
+      auto store_bf16_chunk = [&](const float (&f)[32], __nv_bfloat16* gout, long long ld,
+                                  int col0) {
+        uint8_t* mine = s_stage + lane * 80;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+          uint4 pk;
+          pk.x = pack_bf16x2(f[j], f[j + 1]);
+          pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+          pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
+          pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+          *reinterpret_cast<uint4*>(mine + j * 2) = pk;
+        }
+        __syncwarp();
+        const int piece = lane & 3;
+        if (col0 + piece * 8 < p.N) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = i * 8 + (lane >> 2);
+            if (warp_row0 + r < p.M) {
+              const uint4 val = *reinterpret_cast<const uint4*>(s_stage + r * 80 + piece * 16);
+              *reinterpret_cast<uint4*>(gout + (warp_row0 + r) * ld + col0 + piece * 8) = val;
+            }
+          }
+        }
+        __syncwarp();
+      };
+
       auto process = [&](uint32_t (&v)[32], uint4 (&ax)[4], int c) {
         const int col0 = colbase + c * 32;
-        if (col0 >= p.N) return;  // warp-uniform
+        if (col0 >= p.N || p.debug == 1) return;  // warp-uniform
         float f[32];
         const float4* sb4 = reinterpret_cast<const float4*>(sb + half * HALF_N + c * 32);
 #pragma unroll
@@ -280,20 +316,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
         }
         if (p.act == ACT_GELU) {
-          if (p.out2 != nullptr && row_ok) {
-            __nv_bfloat16* o2 = reinterpret_cast<__nv_bfloat16*>(p.out2) + row * p.ldo2 + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.N) {
-                uint4 pk;
-                pk.x = pack_bf16x2(f[j], f[j + 1]);
-                pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
-                pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
-                pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(o2 + j) = pk;
-              }
-            }
-          }
+          if (p.out2 != nullptr && p.debug != 2)
+            store_bf16_chunk(f, reinterpret_cast<__nv_bfloat16*>(p.out2), p.ldo2, col0);
 #pragma unroll
           for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
         } else if (p.act == ACT_TANH) {
@@ -329,32 +353,23 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
             }
           }
         }
-        if (row_ok) {
+        if (p.debug != 2) {
           if constexpr (OUT_F32) {
-            float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
+            if (row_ok) {
+              float* o = reinterpret_cast<float*>(p.out) + row * p.ldo + col0;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              if (col0 + j < p.N) {
-                if (p.accumulate)
-                  red_add_v4_f32(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
-                else
-                  *reinterpret_cast<float4*>(o + j) =
-                      make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              for (int j = 0; j < 32; j += 4) {
+                if (col0 + j < p.N) {
+                  if (p.accumulate)
+                    red_add_v4_f32(o + j, f[j], f[j + 1], f[j + 2], f[j + 3]);
+                  else
+                    *reinterpret_cast<float4*>(o + j) =
+                        make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+                }
               }
             }
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldo + col0;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              if (col0 + j < p.N) {
-                uint4 pk;
-                pk.x = pack_bf16x2(f[j], f[j + 1]);
-                pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
-                pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
-                pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
-                *reinterpret_cast<uint4*>(o + j) = pk;
-              }
-            }
+            store_bf16_chunk(f, reinterpret_cast<__nv_bfloat16*>(p.out), p.ldo, col0);
           }
         }
       };
@@ -528,6 +543,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   d.wait_epoch = a.wait_epoch;
   d.wait_mult = a.wait_mult;
   d.error_flag = a.error_flag;
+  d.debug = a.debug;
   const int bn = a.block_n ? a.block_n : gemm_pick_block_n(a.M, a.N);
   if (bn == 256) return dispatch_major<256>(a, d, stream);
   if (bn == 128) return dispatch_major<128>(a, d, stream);

@@ -252,7 +252,10 @@ __device__ __forceinline__ float dgelu_erf(float x) {
 // bf16 resolution): one MUFU.RCP + one MUFU.EX2 + 6 FMA instead of libdevice erff.
 __device__ __forceinline__ float erf_exp_fast(float z_abs, float& e_out) {
   // returns erf(z_abs) for z_abs >= 0 and e_out = exp(-z^2)
-  const float t = __frcp_rn(fmaf(0.3275911f, z_abs, 1.0f));
+  // rcp.approx (one MUFU): __frcp_rn expands to MUFU + Newton steps + a slow-path branch per
+  // element, which serialised the whole epilogue (tools/triage_gemm.py: +30 us on FFN1)
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z_abs, 1.0f)));
   float poly = 1.061405429f;
   poly = fmaf(poly, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);

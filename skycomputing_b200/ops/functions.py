@@ -279,8 +279,7 @@ class BertSpanFn(torch.autograd.Function):
                                           sp.g2.grad(), sp.b2n.grad(), dropout_p=p_hid, rng=rng,
                                           rng_stream=sp.rng_base + 3, **wait)
             g2 = dz2d if dz2d is not None else dz2
-            nat.gemm(g2, sv["inter"], a_mn=True, b_mn=True, out=sp.w2.grad(), accumulate=True)
-            nat.colsum_(g2, sp.b2.grad())
+            _wgrad(g2, sv["inter"], sp.w2, sp.b2)
             if sp.has_body:
                 d_h1 = nat.gemm(g2, sp.w2.shadow(), b_mn=True, aux=sv["h1"], act=nat.ACT_DGELU_MUL_AUX)
             else:
@@ -297,8 +296,7 @@ class BertSpanFn(torch.autograd.Function):
             if sp.has_head and len(grads) > 1 and grads[1] is not None:
                 d_a_extra = _flat2d(grads[1]).contiguous()
         if sp.has_body:
-            nat.gemm(d_h1, sv["a"], a_mn=True, b_mn=True, out=sp.w1.grad(), accumulate=True)
-            nat.colsum_(d_h1, sp.b1.grad())
+            _wgrad(d_h1, sv["a"], sp.w1, sp.b1)
             send = _grad_send_kwargs(in_ch, mb, which=0) if not sp.has_head else {}
             d_a = nat.gemm(d_h1, sp.w1.shadow(), b_mn=True, aux=d_a_extra,
                            add_aux=d_a_extra is not None, **send)
@@ -321,13 +319,11 @@ class BertSpanFn(torch.autograd.Function):
                                           sp.g1.grad(), sp.b1n.grad(), dropout_p=p_hid, rng=rng,
                                           rng_stream=sp.rng_base + 2, **wait)
             g1 = dz1d if dz1d is not None else dz1
-            nat.gemm(g1, sv["ctxt"], a_mn=True, b_mn=True, out=sp.wo.grad(), accumulate=True)
-            nat.colsum_(g1, sp.bo.grad())
+            _wgrad(g1, sv["ctxt"], sp.wo, sp.bo)
             dctx = nat.gemm(g1, sp.wo.shadow(), b_mn=True)
             dqkv = nat.attention_bwd(sv["qkv"], sv["mask2"], sv["ctxt"], sv["lse"], dctx, B, S,
                                      sp.heads, dropout_p=p_attn, rng=rng, rng_stream=sp.rng_base + 1)
-            nat.gemm(dqkv, sv["x"], a_mn=True, b_mn=True, out=sp.wqkv.grad(), accumulate=True)
-            nat.colsum_(dqkv, sp.bqkv.grad())
+            _wgrad(dqkv, sv["x"], sp.wqkv, sp.bqkv)
             send = _grad_send_kwargs(in_ch, mb, which=0)
             dx = nat.gemm(dqkv, sp.wqkv.shadow(), b_mn=True, aux=dz1, add_aux=True, **send)
             g_in[0] = None if dx is None else dx.view(B, S, H)
@@ -338,6 +334,37 @@ class BertSpanFn(torch.autograd.Function):
             g_in[1] = d_a.view(B, S, H)
         ctx.saved = None
         return (None, None, None, None, None, None, *g_in, *([None] * (ctx.n_tensors - ctx.n_in)))
+
+
+# Weight-gradient deferral ("B before W"): the input-gradient chain of a stage is on the critical
+# path of the pipeline (the previous stage waits for it), the weight / bias gradients are not.
+# With deferral on, backward only queues them; the engine flushes the queue right after the
+# stage's last dgrad GEMM has published its tiles to the previous stage.
+_DEFER_WGRAD = [False]
+_WGRAD_QUEUE: list = []
+
+
+def set_wgrad_deferral(on: bool) -> None:
+    _DEFER_WGRAD[0] = bool(on)
+    if not on:
+        flush_wgrads()
+
+
+def flush_wgrads() -> None:
+    q = list(_WGRAD_QUEUE)
+    _WGRAD_QUEUE.clear()
+    for g, act, wbank, bbank in q:
+        nat.gemm(g, act, a_mn=True, b_mn=True, out=wbank.grad(), accumulate=True)
+        nat.colsum_(g, bbank.grad())
+
+
+def _wgrad(g: torch.Tensor, act: torch.Tensor, wbank: ParamBank, bbank: ParamBank) -> None:
+    """dW += g^T act (both operands MN-major over the token dimension), db += colsum(g)."""
+    if _DEFER_WGRAD[0]:
+        _WGRAD_QUEUE.append((g, act, wbank, bbank))
+        return
+    nat.gemm(g, act, a_mn=True, b_mn=True, out=wbank.grad(), accumulate=True)
+    nat.colsum_(g, bbank.grad())
 
 
 def _dummy_out(like: torch.Tensor) -> torch.Tensor:

@@ -152,6 +152,7 @@ def gemm(
     error_flag: int = 0,
     block_n: int = 0,
     max_ctas: int = 0,
+    debug: int = 0,
 ) -> Optional[torch.Tensor]:
     """out[M,N] = epilogue(sum_k A[m,k] B[n,k]) on the tcgen05 kernel.
 
@@ -196,7 +197,7 @@ def gemm(
         dropout_p=float(dropout_p), rng_state=0 if rng is None else rng.ptr,
         rng_stream=rng_stream, signal_flags=signal_flags, wait_flags=wait_flags,
         wait_epoch=wait_epoch, wait_mult=wait_mult, error_flag=error_flag, block_n=block_n,
-        max_ctas=max_ctas, stream=_stream(),
+        max_ctas=max_ctas, debug=debug, stream=_stream(),
     )
     return out
 

@@ -86,6 +86,7 @@ class PipelineEngine:
         self._pending_sends: list = []
         self.stage.engine_managed_backward = True
         self.launches_per_step = 0
+        self._defer_wgrad = False
 
     # ------------------------------------------------------------------ setup
     def _native_active(self) -> bool:
@@ -152,6 +153,11 @@ class PipelineEngine:
             # device timers cannot be recorded inside a captured graph
             self.stage._record_forward_time = False
             self.stage._logger = None
+        if multi and self._native_active():
+            from ..ops.functions import set_wgrad_deferral
+
+            self._defer_wgrad = True
+            set_wgrad_deferral(True)
         self._order = (one_f_one_b_order if self.schedule == "1f1b" else sequential_order)(
             self.s, self.P, self.m)
         self._setup_done = True
@@ -218,6 +224,10 @@ class PipelineEngine:
                     ts.append(o)
                     gs.append(g.to(o.dtype))
             torch.autograd.backward(ts, gs)
+        if self._defer_wgrad:
+            from ..ops.functions import flush_wgrads
+
+            flush_wgrads()  # weight grads run AFTER the input gradient went upstream
         st.end_backward()
         if self.is_first or self.in_fused:
             return None
