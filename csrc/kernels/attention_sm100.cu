@@ -20,6 +20,7 @@
 #include <stdint.h>
 
 #include "api.h"
+#include "launch_util.h"
 #include "sm100_ptx.cuh"
 
 namespace sky {
@@ -89,6 +90,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnDev
     tmem_alloc(tmem_ptr_smem, 256);
     tmem_relinquish();
   }
+  pdl_wait();
+  pdl_launch_dependents();
   sMask[tid] = p.mask ? p.mask[b * kS + tid] * kLog2e : 0.f;
   tcgen05_fence_before();
   __syncthreads();
@@ -252,6 +255,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
     tmem_alloc(tmem_ptr_smem, 256);
     tmem_relinquish();
   }
+  pdl_wait();
+  pdl_launch_dependents();
   sMask[tid] = p.mask ? p.mask[b * kS + tid] * kLog2e : 0.f;
   tcgen05_fence_before();
   __syncthreads();
@@ -461,7 +466,8 @@ int launch_attention_fwd(const AttnArgs& a, cudaStream_t stream) {
   d.dropout_p = a.dropout_p;
   d.rng_state = a.rng_state;
   d.rng_stream = a.rng_stream;
-  attention_fwd_kernel<<<a.B * a.heads, 128, kFwdSmem, stream>>>(tm, d);
+  cudaError_t le = launch_pdl(attention_fwd_kernel, dim3(a.B * a.heads), dim3(128), kFwdSmem, stream, tm, d);
+  if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
 
@@ -498,7 +504,8 @@ int launch_attention_bwd(const AttnArgs& a, cudaStream_t stream) {
   d.dropout_p = a.dropout_p;
   d.rng_state = a.rng_state;
   d.rng_stream = a.rng_stream;
-  attention_bwd_kernel<<<a.B * a.heads, 128, kBwdSmem, stream>>>(tm, tdo, d);
+  cudaError_t le = launch_pdl(attention_bwd_kernel, dim3(a.B * a.heads), dim3(128), kBwdSmem, stream, tm, tdo, d);
+  if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
 

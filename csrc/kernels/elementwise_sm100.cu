@@ -15,6 +15,7 @@
 #include <stdint.h>
 
 #include "api.h"
+#include "launch_util.h"
 #include "sm100_ptx.cuh"
 
 namespace sky {
@@ -53,6 +54,8 @@ layernorm_fwd_kernel(const __nv_bfloat16* __restrict__ z, __nv_bfloat16* __restr
                      const float* __restrict__ gamma, const float* __restrict__ beta, int M, int H,
                      float eps, const uint32_t* wait_flags, const uint32_t* wait_epoch,
                      uint32_t wait_mult, int* error_flag, uint32_t* signal_flags) {
+  pdl_wait();
+  pdl_launch_dependents();
   // Each CTA owns kLnRowsPerCta consecutive rows (8 warps x 4 rows) so that a finished CTA can
   // publish "32 rows of panel p are written" with one release.sys add (y may be peer memory).
   const int lane = threadIdx.x & 31;
@@ -147,6 +150,8 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
                      __nv_bfloat16* __restrict__ dz_dropped, int M, int H, float dropout_p,
                      const uint64_t* rng_state, uint32_t rng_stream, const uint32_t* wait_flags,
                      const uint32_t* wait_epoch, uint32_t wait_mult, int* error_flag) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int lane = threadIdx.x & 31;
   const int warps_per_block = blockDim.x >> 5;
   const int warp_global = blockIdx.x * warps_per_block + (threadIdx.x >> 5);
@@ -243,6 +248,8 @@ __global__ void __launch_bounds__(256)
 ln_param_grad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
                      float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int H) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float redg[8][256 + 8];
   __shared__ float redb[8][256 + 8];
   const int cg = threadIdx.x & 31;
@@ -293,6 +300,8 @@ ln_param_grad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x, int M, int N, long long ldx,
               float* __restrict__ out) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float red[8][256 + 8];
   const int cg = threadIdx.x & 31;
   const int rl = threadIdx.x >> 5;
@@ -763,6 +772,8 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float*
 __global__ void __launch_bounds__(256)
 dgelu_mul_kernel(const uint4* __restrict__ g, const uint4* __restrict__ h, uint4* __restrict__ y,
                  long long n8) {
+  pdl_wait();
+  pdl_launch_dependents();
   for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n8;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
     const uint4 a = g[i];
@@ -845,7 +856,7 @@ int launch_layernorm_fwd(const LayerNormFwdArgs& a, cudaStream_t stream) {
   const int grid = (a.M + kLnRowsPerCta - 1) / kLnRowsPerCta;
   const int nv = (a.H / 8 + 31) / 32;
 #define SKY_LN_FWD(NV)                                                                          \
-  layernorm_fwd_kernel<NV><<<grid, 256, 0, stream>>>(                                           \
+  launch_pdl(layernorm_fwd_kernel<NV>, dim3(grid), dim3(256), 0, stream,                        \
       reinterpret_cast<const __nv_bfloat16*>(a.z), reinterpret_cast<__nv_bfloat16*>(a.y), a.mean, \
       a.rstd, a.gamma, a.beta, a.M, a.H, a.eps, a.wait_flags, a.wait_epoch, a.wait_mult,        \
       a.error_flag, a.signal_flags)
@@ -863,7 +874,7 @@ int launch_layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t stream) {
   const int grid = grid_for_rows(a.M, 8, 148 * 8);
   const int nv = (a.H / 8 + 31) / 32;
 #define SKY_LN_BWD(NV)                                                                           \
-  layernorm_bwd_kernel<NV><<<grid, 256, 0, stream>>>(                                            \
+  launch_pdl(layernorm_bwd_kernel<NV>, dim3(grid), dim3(256), 0, stream,                         \
       reinterpret_cast<const __nv_bfloat16*>(a.dy), reinterpret_cast<const __nv_bfloat16*>(a.z), \
       a.mean, a.rstd, a.gamma, reinterpret_cast<__nv_bfloat16*>(a.dz),                           \
       reinterpret_cast<__nv_bfloat16*>(a.dz_dropped), a.M, a.H, a.dropout_p, a.rng_state,        \
@@ -882,7 +893,7 @@ int launch_layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t stream) {
     if (ry < 1) ry = 1;
     g2.y = ry;
     // NOTE: when gated on peer flags, the row kernel above has already waited for every panel.
-    ln_param_grad_kernel<<<g2, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(a.dy),
+    launch_pdl(ln_param_grad_kernel, g2, dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(a.dy),
                                                  reinterpret_cast<const __nv_bfloat16*>(a.z),
                                                  a.mean, a.rstd, a.dgamma, a.dbeta, a.M, a.H);
   }
@@ -894,7 +905,7 @@ int launch_dgelu_mul(const void* g, const void* h, void* y, long long n, cudaStr
   if (n % 8 != 0) return 914;
   long long blocks = (n / 8 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  dgelu_mul_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(
+  launch_pdl(dgelu_mul_kernel, dim3(static_cast<unsigned>(blocks)), dim3(256), 0, stream,
       reinterpret_cast<const uint4*>(g), reinterpret_cast<const uint4*>(h),
       reinterpret_cast<uint4*>(y), n / 8);
   SKY_LAUNCH_CHECK();
@@ -907,7 +918,7 @@ int launch_colsum(const void* x, int M, int N, int ldx, float* out, cudaStream_t
   int ry = (M + 63) / 64;
   if (ry > 64) ry = 64;
   grid.y = ry;
-  colsum_kernel<<<grid, 256, 0, stream>>>(reinterpret_cast<const __nv_bfloat16*>(x), M, N, ldx,
+  launch_pdl(colsum_kernel, grid, dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(x), M, N, static_cast<long long>(ldx),
                                           out);
   SKY_LAUNCH_CHECK();
 }

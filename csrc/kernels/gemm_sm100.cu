@@ -27,6 +27,7 @@
 #include <mutex>
 
 #include "api.h"
+#include "launch_util.h"
 #include "sm100_ptx.cuh"
 
 namespace sky {
@@ -126,6 +127,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  // everything above (barrier init, TMEM alloc, tensormap prefetch) overlapped the previous
+  // kernel's tail; from here on we read what it produced
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp_idx == 0 && lane == 0) {
     // ===================================== TMA producer =====================================
@@ -495,7 +500,8 @@ int launch_inst(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
   const int num_tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BLOCK_N - 1) / BLOCK_N);
   int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
   if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
-  kern<<<grid, kNumThreads, C::kSmemBytes, stream>>>(tma, tmb, dev);
+  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kNumThreads), C::kSmemBytes, stream, tma, tmb, dev);
+  if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
 

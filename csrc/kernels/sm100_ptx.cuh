@@ -39,6 +39,13 @@ __device__ __forceinline__ uint64_t globaltimer_ns() {
   return t;
 }
 
+// Programmatic dependent launch: wait until the previous grid in the stream has completed (and its
+// memory is visible); allow the next grid to start launching.  No-ops without the launch attribute.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ----------------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------------

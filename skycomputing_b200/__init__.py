@@ -6,7 +6,21 @@ Worker / WorkerManager), ``RpcModel``, ``Runner`` + hooks, ``Logger``, ``Distrib
 ``Stimulator`` - on a Blackwell-first substrate (one process per GPU, hand-written sm_100a
 kernels, peer-memory fused stage boundaries over NVLink 5, C++ allocator / benchmark loop).
 """
-from .builder import *  # noqa: F401,F403
+def _ensure_core() -> None:
+    """The C++ core (allocator / stimulator) is a hard dependency of `dynamics`; build it on first
+    import if the in-tree .so is missing (g++ only, a few seconds).  The CUDA module is built by
+    `__graft_entry__.build()` / `python -m skycomputing_b200._build` and is only needed on GPUs."""
+    try:
+        from . import _core  # noqa: F401
+    except ImportError:
+        from . import _build
+
+        _build.build_core(verbose=False)
+
+
+_ensure_core()
+
+from .builder import *  # noqa: F401,F403,E402
 from .config import *  # noqa: F401,F403
 from .dataset import *  # noqa: F401,F403
 from .dynamics import *  # noqa: F401,F403

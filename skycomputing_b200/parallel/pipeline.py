@@ -211,6 +211,11 @@ class PipelineEngine:
         st.microbatch = j
         st.in_channel = self.fused.prev if self.in_fused else None
         st.out_channel = self.fused.next if self.out_fused else None
+        # Weight gradients of the PREVIOUS micro-batch run now, i.e. in front of the kernel that
+        # will wait for this micro-batch's incoming gradient: during the 1F1B cool-down they fill
+        # what would otherwise be pipeline bubble, and they never delay the input gradient that
+        # the previous stage is waiting for.
+        self._flush_wgrads()
         st.begin_backward()
         if self.is_last:
             loss.backward()
@@ -224,14 +229,16 @@ class PipelineEngine:
                     ts.append(o)
                     gs.append(g.to(o.dtype))
             torch.autograd.backward(ts, gs)
-        if self._defer_wgrad:
-            from ..ops.functions import flush_wgrads
-
-            flush_wgrads()  # weight grads run AFTER the input gradient went upstream
         st.end_backward()
         if self.is_first or self.in_fused:
             return None
         return self._in_grads(args)
+
+    def _flush_wgrads(self) -> None:
+        if self._defer_wgrad:
+            from ..ops.functions import flush_wgrads
+
+            flush_wgrads()
 
     # ------------------------------------------------------------------ comm helpers (unfused)
     @staticmethod
@@ -339,6 +346,7 @@ class PipelineEngine:
                         pending_in = self._send_backward_recv_forward(in_grads)
                     else:
                         self._send_backward(in_grads)
+        self._flush_wgrads()
         self.optimizer.step()
         if self.comm is not None:
             self.comm.wait(self._pending_sends)
