@@ -242,6 +242,8 @@ def run_ours(args) -> dict:
     else:
         launches = int(graph_launches)
     err = eng.fused.error_code() if eng.fused is not None else 0
+    if os.environ.get("SKY_TRACE", "0") == "1":
+        _dump_trace(eng, rank, world, device, N)
     result = None
     if rank == 0:
         value = global_batch * args.steps / (dev_ms * 1e-3)
@@ -274,6 +276,38 @@ def run_ours(args) -> dict:
     eng.close()
     dist.destroy_process_group()
     return result
+
+
+def _dump_trace(eng, rank, world, device, N):
+    """SKY_TRACE=1: write the device timeline of the last step (tools/render_trace.py draws it).
+    GPU %globaltimer clocks are aligned with barrier-bracketed stamps (median of 15)."""
+    import json as _json
+
+    import torch
+    import torch.distributed as dist
+    from skycomputing_b200.ops import native as nat
+
+    slot = torch.zeros(1, dtype=torch.int64, device=device)
+    offs = []
+    for _ in range(15):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        nat.ext().record_time(slot.data_ptr(), torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        t = torch.tensor([slot.item()], dtype=torch.int64, device=device)
+        if world > 1:
+            g = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(g, t)
+            offs.append(int(t.item() - g[0].item()))
+        else:
+            offs.append(0)
+    offs.sort()
+    out_dir = os.path.join(ROOT, "gpurun_out", "trace")
+    os.makedirs(out_dir, exist_ok=True)
+    with open(os.path.join(out_dir, f"n{N}_rank{rank}.json"), "w") as f:
+        _json.dump({"rank": rank, "stage": eng.s, "clock_offset_ns": offs[len(offs) // 2],
+                    "events": [[list(tag), ns] for tag, ns in eng.trace()]}, f)
 
 
 def main():

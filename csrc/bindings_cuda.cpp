@@ -42,7 +42,7 @@ void gemm(uintptr_t A, uintptr_t B, int M, int N, int K, int lda, int ldb, bool 
           uintptr_t out, int ldo, bool out_f32, bool accumulate, uintptr_t out2, int ldo2,
           uintptr_t bias, uintptr_t aux, int ldaux, int act, bool add_aux, float dropout_p,
           uintptr_t rng_state, uint32_t rng_stream, uintptr_t signal_flags, uintptr_t wait_flags,
-          uintptr_t wait_epoch, uint32_t wait_mult, uintptr_t error_flag, int block_n, int max_ctas,
+          uintptr_t wait_epoch, uint32_t wait_mult, uintptr_t error_flag, int block_n, int pair, int stream_k, int max_ctas,
           int debug,
           uintptr_t stream) {
   GemmArgs a;
@@ -75,6 +75,8 @@ void gemm(uintptr_t A, uintptr_t B, int M, int N, int K, int lda, int ldb, bool 
   a.wait_mult = wait_mult;
   a.error_flag = P<int>(error_flag);
   a.block_n = block_n;
+  a.pair = pair;
+  a.stream_k = stream_k;
   a.max_ctas = max_ctas;
   a.debug = debug;
   check(sky::launch_gemm(a, S(stream)), "gemm");
@@ -356,7 +358,7 @@ PYBIND11_MODULE(_cuda, m) {
         py::arg("ldaux") = 0, py::arg("act") = 0, py::arg("add_aux") = false,
         py::arg("dropout_p") = 0.f, py::arg("rng_state") = 0, py::arg("rng_stream") = 0,
         py::arg("signal_flags") = 0, py::arg("wait_flags") = 0, py::arg("wait_epoch") = 0,
-        py::arg("wait_mult") = 0, py::arg("error_flag") = 0, py::arg("block_n") = 0,
+        py::arg("wait_mult") = 0, py::arg("error_flag") = 0, py::arg("block_n") = 0, py::arg("pair") = -1, py::arg("stream_k") = -1,
         py::arg("max_ctas") = 0, py::arg("debug") = 0, py::arg("stream") = 0);
   m.def("gemm_pick_block_n", &sky::gemm_pick_block_n);
   m.def("gemm_tiles_per_panel", &sky::gemm_tiles_per_panel);

@@ -47,6 +47,8 @@ struct GemmArgs {
   uint32_t wait_mult = 0;
   int* error_flag = nullptr;  // set to non-zero on flag-wait timeout
   int block_n = 0;            // 0 = auto (128 or 256)
+  int stream_k = -1;          // stream-K schedule: -1 auto, 0 off, 1 on
+  int pair = -1;              // -1 auto, 0 single CTAs, 1 cta_group::2 pairs, 2 = 4-CTA clusters: two pairs + A multicast
   int debug = 0;              // perf triage: 1 = epilogue discards the tile, 2 = epilogue math but no stores
   int max_ctas = 0;           // 0 = all SMs
 };
@@ -55,6 +57,8 @@ struct GemmArgs {
 int launch_gemm(const GemmArgs& args, cudaStream_t stream);
 int gemm_tiles_per_panel(int N, int block_n);  // number of signals per 128-row panel
 int gemm_pick_block_n(int M, int N);
+bool gemm_pick_pair(int M, int N, int K);
+bool gemm_pick_quad(int M, int N, int K);
 
 // ---------------------------------------------------------------------------------------------
 // LayerNorm (rows of H), bf16 in/out, fp32 statistics

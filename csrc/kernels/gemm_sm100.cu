@@ -24,7 +24,10 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <cstdlib>
+#include <map>
 #include <mutex>
+#include <utility>
 
 #include "api.h"
 #include "launch_util.h"
@@ -41,11 +44,14 @@ constexpr int kNumThreads = 384;  // warp0 TMA, warp1 MMA, warp2 TMEM alloc, war
 constexpr int kEpiWarp0 = 4;
 constexpr uint64_t kFlagTimeoutNs = 4000000000ull;  // 4 s
 
-template <int BLOCK_N>
+// PAIR: two CTAs (cluster of 2, cta_group::2) compute one 256 x BLOCK_N tile; each stages its own
+// 128 rows of A and half of the B tile.
+template <int BLOCK_N, bool PAIR>
 struct Cfg {
-  static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
+  static constexpr int kBRows = PAIR ? BLOCK_N / 2 : BLOCK_N;  // B rows staged by ONE CTA
+  static constexpr int kStages = PAIR ? (BLOCK_N == 256 ? 6 : 8) : (BLOCK_N == 256 ? 4 : 6);
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 2;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 2;
+  static constexpr int kBBytes = kBRows * BLOCK_K * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 256 or 512 (power of two)
   static constexpr int kBiasBytes = 2 * BLOCK_N * 4;  // double-buffered bias tile
@@ -73,14 +79,80 @@ struct GemmDev {
   uint32_t wait_mult;
   int* error_flag;
   int debug;
+  // stream-K: the flattened (tile, k-block) space is cut into one contiguous range per CTA (pair);
+  // tiles shared by several CTAs are reduced through `ws` by whichever CTA arrives last
+  int stream_k;
+  float* ws;           // partial accumulators: slot (2 * unit + which) * ctas_per_unit + cta_rank
+  uint32_t* counters;  // per CTA tile: [2 * t] arrivals, [2 * t + 1] partials written
 };
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32>
+struct Work {
+  int tile, kb0, kb1;
+};
+
+// Tile scheduler shared by the three warp roles.  Classic mode: tiles unit, unit + U, ... with the
+// whole K range.  Stream-K mode: k-blocks [unit * T / U, (unit + 1) * T / U) of T = tiles * nk.
+struct Sched {
+  int stream, unit, num_units, num_tiles, nk;
+  long long total;
+  int pos, end, tile;
+  __device__ __forceinline__ long long bound(int u) const { return u * total / num_units; }
+  __device__ __forceinline__ void init(int stream_k, int unit_, int num_units_, int num_tiles_,
+                                       int nk_) {
+    stream = stream_k;
+    unit = unit_;
+    num_units = num_units_;
+    num_tiles = num_tiles_;
+    nk = nk_;
+    total = static_cast<long long>(num_tiles_) * nk_;
+    pos = static_cast<int>(bound(unit_));
+    end = static_cast<int>(bound(unit_ + 1));
+    tile = unit_ - num_units_;
+  }
+  __device__ __forceinline__ bool next(Work& w) {
+    if (!stream) {
+      tile += num_units;
+      if (tile >= num_tiles) return false;
+      w.tile = tile;
+      w.kb0 = 0;
+      w.kb1 = nk;
+      return true;
+    }
+    if (pos >= end) return false;
+    w.tile = pos / nk;
+    w.kb0 = pos - w.tile * nk;
+    const int len = min(nk - w.kb0, end - pos);
+    w.kb1 = w.kb0 + len;
+    pos += len;
+    return true;
+  }
+  // unit whose range contains flattened position x
+  __device__ __forceinline__ int unit_of(long long x) const {
+    int u = static_cast<int>(x * num_units / total);
+    while (u + 1 < num_units && bound(u + 1) <= x) ++u;
+    while (u > 0 && bound(u) > x) --u;
+    return u;
+  }
+  __device__ __forceinline__ int first_tile(int u) const { return static_cast<int>(bound(u) / nk); }
+};
+
+// CL = CTAs per cluster: 1 = independent CTAs, 2 = one cta_group::2 pair, 4 = two pairs that work
+// on the same 256 rows and neighbouring N tiles and MULTICAST the A operand to each other (each
+// CTA fetches half of its 128 A rows from L2 and TMA delivers them to itself and to the CTA of
+// the other pair that needs the same rows).
+template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32, int CL>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
-  using C = Cfg<BLOCK_N>;
+  constexpr bool PAIR = CL >= 2;
+  constexpr bool MC = CL == 4;
+  using C = Cfg<BLOCK_N, PAIR>;
   constexpr int kStages = C::kStages;
+  const uint32_t cl_rank = PAIR ? cluster_ctarank() : 0u;  // rank in the cluster
+  const uint32_t cta_rank = cl_rank & 1u;                  // rank in the pair
+  const uint32_t pair_idx = cl_rank >> 1;                  // which pair of the cluster (MC)
+  const uint32_t leader_rank = cl_rank & ~1u;              // cluster rank of this pair's leader
+  const bool leader = cta_rank == 0;
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment.
@@ -99,10 +171,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   const int warp_idx = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int num_m_blks = (p.M + BLOCK_M - 1) / BLOCK_M;
+  // tile scheduler: a "unit" is one CTA (128 rows) or one CTA pair (256 rows)
+  constexpr int UNIT_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
+  const int num_m_units = (p.M + UNIT_M - 1) / UNIT_M;
   const int num_n_blks = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int num_tiles = num_m_blks * num_n_blks;
+  // MC: a scheduling unit covers TWO neighbouring N tiles (one per pair); the host only selects
+  // this mode when the number of N tiles is even
+  const int num_n_units = MC ? num_n_blks / 2 : num_n_blks;
+  const int num_tiles = num_m_units * num_n_units;
   const int num_k_blks = (p.K + BLOCK_K - 1) / BLOCK_K;
+  const int unit_id = static_cast<int>(blockIdx.x) / CL;
+  const int num_units = static_cast<int>(gridDim.x) / CL;
 
   if (warp_idx == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -111,20 +190,31 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   if (warp_idx == 1 && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      // MC: a stage is written by two CTAs' multicasts, so BOTH pairs' MMAs must have released it
+      mbar_init(&empty_bar[i], MC ? 2 : 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full_bar[i], 1);
-      mbar_init(&tmem_empty_bar[i], 8);  // one arrive per epilogue warp
+      // one arrive per epilogue warp (of both CTAs in pair mode: the leader's barrier is used)
+      mbar_init(&tmem_empty_bar[i], PAIR ? 16 : 8);
     }
     fence_barrier_init();
   }
   if (warp_idx == 2) {
-    tmem_alloc(tmem_ptr_smem, C::kTmemCols);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_ptr_smem, C::kTmemCols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr_smem, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if constexpr (PAIR)
+    cluster_sync_all();  // the peer's barriers must be initialised before anything signals them
+  else
+    __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   // everything above (barrier init, TMEM alloc, tensormap prefetch) overlapped the previous
@@ -136,36 +226,68 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     // ===================================== TMA producer =====================================
     int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_blk = tile % num_m_blks;
-      const int n_blk = tile / num_m_blks;
-      if (p.wait_flags != nullptr) {
+    // pair mode: both CTAs' loads complete on the LEADER's full barrier (cluster address)
+    const uint32_t full_addr0 = PAIR ? mapa_shared(smem_u32(&full_bar[0]), leader_rank) : 0u;
+    // multicast loads name the barrier by its CTA-relative address with the peer bit cleared:
+    // every destination CTA's pair leader receives the bytes that landed in that destination
+    const uint32_t full_mc0 = smem_u32(&full_bar[0]) & 0xFEFFFFFFu;
+    const uint16_t mc_mask = static_cast<uint16_t>((1u << cl_rank) | (1u << (cl_rank ^ 2u)));
+    Sched sched;
+    sched.init(p.stream_k, unit_id, num_units, num_tiles, num_k_blks);
+    Work w;
+    while (sched.next(w)) {
+      const int tile = w.tile;
+      const int m_blk = (tile % num_m_units) * (PAIR ? 2 : 1) + static_cast<int>(cta_rank);
+      const int n_blk = (tile / num_m_units) * (MC ? 2 : 1) + (MC ? static_cast<int>(pair_idx) : 0);
+      const int b_row0 = n_blk * BLOCK_N + static_cast<int>(cta_rank) * C::kBRows;
+      if (p.wait_flags != nullptr && m_blk * BLOCK_M < p.M) {
         const uint32_t target = (*p.wait_epoch) * p.wait_mult;
         if (!wait_flag_ge(p.wait_flags + m_blk, target, kFlagTimeoutNs)) {
           if (p.error_flag) atomicExch(p.error_flag, 1);
         }
         fence_proxy_async();  // peer generic-proxy writes -> our async-proxy (TMA) reads
       }
-      for (int kb = 0; kb < num_k_blks; ++kb) {
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
-        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+        if (!PAIR && p.debug == 3) {  // triage: no loads at all, the MMAs chew on stale smem
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
+        if (leader) mbar_expect_tx(&full_bar[stage], (PAIR ? 2 : 1) * C::kStageBytes);
         uint8_t* sa = smem_a + stage * C::kABytes;
         uint8_t* sb = smem_b + stage * C::kBBytes;
-        if constexpr (!A_MN) {
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * BLOCK_K, m_blk * BLOCK_M);
+        auto load = [&](uint8_t* dst, const CUtensorMap* tm, int c0, int c1) {
+          if constexpr (PAIR)
+            tma_load_2d_pair(dst, tm, full_addr0 + stage * 8, c0, c1);
+          else
+            tma_load_2d(dst, tm, &full_bar[stage], c0, c1);
+        };
+        if constexpr (MC) {
+          // my half (64 rows) of the A tile, delivered to me and to the CTA of the other pair
+          const int h = static_cast<int>(pair_idx);
+          if constexpr (!A_MN)
+            tma_load_2d_pair_mc(sa + h * (64 * 128), &tmap_a, full_mc0 + stage * 8, kb * BLOCK_K,
+                                m_blk * BLOCK_M + h * 64, mc_mask);
+          else
+            tma_load_2d_pair_mc(sa + h * (BLOCK_K * 128), &tmap_a, full_mc0 + stage * 8,
+                                m_blk * BLOCK_M + h * 64, kb * BLOCK_K, mc_mask);
+        } else if constexpr (!A_MN) {
+          load(sa, &tmap_a, kb * BLOCK_K, m_blk * BLOCK_M);
         } else {
 #pragma unroll
           for (int c = 0; c < BLOCK_M / 64; ++c)
-            tma_load_2d(sa + c * (BLOCK_K * 128), &tmap_a, &full_bar[stage],
-                        m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
+            load(sa + c * (BLOCK_K * 128), &tmap_a, m_blk * BLOCK_M + c * 64, kb * BLOCK_K);
         }
         if constexpr (!B_MN) {
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * BLOCK_K, n_blk * BLOCK_N);
+          load(sb, &tmap_b, kb * BLOCK_K, b_row0);
         } else {
 #pragma unroll
-          for (int c = 0; c < BLOCK_N / 64; ++c)
-            tma_load_2d(sb + c * (BLOCK_K * 128), &tmap_b, &full_bar[stage],
-                        n_blk * BLOCK_N + c * 64, kb * BLOCK_K);
+          for (int c = 0; c < C::kBRows / 64; ++c)
+            load(sb + c * (BLOCK_K * 128), &tmap_b, b_row0 + c * 64, kb * BLOCK_K);
         }
         if (++stage == kStages) {
           stage = 0;
@@ -173,9 +295,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
     }
-  } else if (warp_idx == 1 && lane == 0) {
+  } else if (warp_idx == 1 && lane == 0 && leader) {
     // ===================================== MMA issuer ======================================
-    constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    constexpr uint32_t idesc = make_idesc_bf16_f32(UNIT_M, BLOCK_N, A_MN, B_MN);
     // K-major  SW128: 8-row atoms 1024B apart (SBO), LBO unused (1); K advance = 32B per UMMA_K
     // MN-major SW128: 64-element MN chunks BLOCK_K*128B apart (LBO), 8-k-row groups 1024B apart
     //                 (SBO); K advance = 16 rows * 128B = 2048B per UMMA_K
@@ -186,26 +308,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    Sched sched;
+    sched.init(p.stream_k, unit_id, num_units, num_tiles, num_k_blks);
+    Work w;
+    for (; sched.next(w); ++it) {
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);
       tcgen05_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
-      for (int kb = 0; kb < num_k_blks; ++kb) {
+      for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
+        if (!PAIR && p.debug == 4) {  // triage: loads only, no MMA
+          mbar_arrive(&empty_bar[stage]);
+          if (kb == w.kb1 - 1) mbar_arrive(&tmem_full_bar[acc]);
+          if (++stage == kStages) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         const uint64_t desc_a =
             make_smem_desc_sw128(smem_u32(smem_a + stage * C::kABytes), a_lbo, 1024);
         const uint64_t desc_b =
             make_smem_desc_sw128(smem_u32(smem_b + stage * C::kBBytes), b_lbo, 1024);
 #pragma unroll
         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          umma_bf16_ss(tmem_d, desc_a + k * a_kadv, desc_b + k * b_kadv, idesc,
-                       (kb | k) != 0 ? 1u : 0u);
+          if constexpr (PAIR)
+            umma_bf16_ss_pair(tmem_d, desc_a + k * a_kadv, desc_b + k * b_kadv, idesc,
+                              (kb != w.kb0 || k != 0) ? 1u : 0u);
+          else
+            umma_bf16_ss(tmem_d, desc_a + k * a_kadv, desc_b + k * b_kadv, idesc,
+                         (kb != w.kb0 || k != 0) ? 1u : 0u);
         }
-        umma_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
-        if (kb == num_k_blks - 1) umma_commit(&tmem_full_bar[acc]);
+        // smem slot reusable (in both CTAs) once these MMAs retire
+        if constexpr (PAIR) {
+          const uint16_t pair_mask = static_cast<uint16_t>(3u << leader_rank);
+          umma_commit_pair(&empty_bar[stage], MC ? static_cast<uint16_t>(0xF) : pair_mask);
+          if (kb == w.kb1 - 1) umma_commit_pair(&tmem_full_bar[acc], pair_mask);
+        } else {
+          umma_commit(&empty_bar[stage]);
+          if (kb == w.kb1 - 1) umma_commit(&tmem_full_bar[acc]);
+        }
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -241,9 +386,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       drop_scale = 1.f / (1.f - p.dropout_p);
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m_blk = tile % num_m_blks;
-      const int n_blk = tile / num_m_blks;
+    const uint32_t tmem_empty_addr0 =
+        PAIR ? mapa_shared(smem_u32(&tmem_empty_bar[0]), leader_rank)
+             : smem_u32(&tmem_empty_bar[0]);
+    Sched sched;
+    sched.init(p.stream_k, unit_id, num_units, num_tiles, num_k_blks);
+    Work w;
+    uint32_t* s_ticket = tmem_ptr_smem + 1;
+    constexpr int kCtasPerUnit = CL;
+    constexpr int kTileElems = BLOCK_M * BLOCK_N;
+    for (; sched.next(w); ++it) {
+      const int tile = w.tile;
+      const int m_blk = (tile % num_m_units) * (PAIR ? 2 : 1) + static_cast<int>(cta_rank);
+      const int n_blk = (tile / num_m_units) * (MC ? 2 : 1) + (MC ? static_cast<int>(pair_idx) : 0);
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       const long long row = static_cast<long long>(m_blk) * BLOCK_M + row_in_tile;
@@ -273,6 +428,49 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       tcgen05_fence_after();
       const uint32_t taddr =
           tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BLOCK_N + half * HALF_N;
+
+      // ---- stream-K: is this CTA the one that finishes the tile? ----
+      // Every contributor takes a ticket once its share of the K range sits in TMEM.  All but the
+      // last arrival park their raw fp32 accumulators in the workspace and bump `done`; the last
+      // arrival waits for those writes (the writers are already past their main loop, so the
+      // wait is short and cannot deadlock), adds them and runs the real epilogue.
+      bool finisher = true;
+      int n_contrib = 1, u_first = 0;
+      float* ws_mine = nullptr;
+      const bool partial = p.stream_k && !(w.kb0 == 0 && w.kb1 == num_k_blks) && !p.accumulate;
+      const int ctile = n_blk * (num_m_units * (PAIR ? 2 : 1)) + m_blk;
+      if (partial) {
+        u_first = sched.unit_of(static_cast<long long>(tile) * num_k_blks);
+        const int u_last = sched.unit_of(static_cast<long long>(tile + 1) * num_k_blks - 1);
+        n_contrib = u_last - u_first + 1;
+        if (epi_tid == 0) *s_ticket = atomicAdd(p.counters + 2 * ctile, 1u);
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        finisher = (*s_ticket == static_cast<uint32_t>(n_contrib - 1));
+        const int which = (tile == sched.first_tile(unit_id)) ? 0 : 1;
+        ws_mine = p.ws + static_cast<size_t>((2 * unit_id + which) * kCtasPerUnit + cl_rank) *
+                             kTileElems;
+        if (finisher) {
+          if (epi_tid == 0) {
+            const uint64_t t0 = globaltimer_ns();
+            while (ld_acquire_sys(p.counters + 2 * ctile + 1) <
+                   static_cast<uint32_t>(n_contrib - 1)) {
+              if (globaltimer_ns() - t0 > kFlagTimeoutNs) {
+                if (p.error_flag) atomicExch(p.error_flag, 2);
+                break;
+              }
+            }
+            p.counters[2 * ctile] = 0;  // leave the counters clean for the next launch
+            p.counters[2 * ctile + 1] = 0;
+          }
+          asm volatile("bar.sync 1, 256;" ::: "memory");
+        }
+      }
+      // workspace layout of one 128 x BLOCK_N tile: [column / 4][row][4] floats, so that the 32
+      // lanes (= 32 rows) of a warp touch 512 contiguous bytes per float4 access
+      auto ws_ptr = [&](float* base, int c) {
+        return reinterpret_cast<float4*>(base) + ((half * HALF_N + c * 32) >> 2) * BLOCK_M +
+               row_in_tile;
+      };
 
       // bf16 stores go through a per-warp smem transpose: a lane owns one accumulator ROW, so
       // storing straight from registers makes every STG.128 touch 32 different rows (32 partial
@@ -309,7 +507,33 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
 
       auto process = [&](uint32_t (&v)[32], uint4 (&ax)[4], int c) {
         const int col0 = colbase + c * 32;
-        if (col0 >= p.N || p.debug == 1) return;  // warp-uniform
+        if (col0 >= p.N || p.debug == 1 || p.debug >= 3) return;  // warp-uniform
+        if (partial) {
+          if (!finisher) {
+            float4* wp = ws_ptr(ws_mine, c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              wp[j * BLOCK_M] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                            __uint_as_float(v[4 * j + 2]),
+                                            __uint_as_float(v[4 * j + 3]));
+            return;
+          }
+          for (int u = u_first; u < u_first + n_contrib; ++u) {
+            if (u == unit_id) continue;
+            const int which_u = (tile == sched.first_tile(u)) ? 0 : 1;
+            const float4* rp = ws_ptr(
+                p.ws + static_cast<size_t>((2 * u + which_u) * kCtasPerUnit + cl_rank) * kTileElems,
+                c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 x = __ldcg(rp + j * BLOCK_M);
+              v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + x.x);
+              v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + x.y);
+              v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + x.z);
+              v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + x.w);
+            }
+          }
+        }
         float f[32];
         const float4* sb4 = reinterpret_cast<const float4*>(sb + half * HALF_N + c * 32);
 #pragma unroll
@@ -397,8 +621,19 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       // release the TMEM buffer back to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-      if (p.signal_flags != nullptr) {
+      if (lane == 0) {
+        if constexpr (PAIR)
+          mbar_arrive_cluster(tmem_empty_addr0 + acc * 8);
+        else
+          mbar_arrive(&tmem_empty_bar[acc]);
+      }
+      if (partial && !finisher) {
+        // publish the parked partial: all stores -> fence -> barrier -> one counter bump
+        __threadfence();
+        asm volatile("bar.sync 2, 256;" ::: "memory");
+        if (epi_tid == 0) atomicAdd(p.counters + 2 * ctile + 1, 1u);
+      }
+      if (finisher && p.signal_flags != nullptr && m_blk * BLOCK_M < p.M) {
         // publish this tile: all 256 epilogue threads' stores -> barrier -> one release.sys
         __threadfence_system();
         asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -408,10 +643,17 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  __syncwarp();
+  if constexpr (PAIR)
+    cluster_sync_all();  // neither CTA may leave while the other still signals / reads it
+  else
+    __syncthreads();
   if (warp_idx == 2) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if constexpr (PAIR)
+      tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else
+      tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -463,28 +705,144 @@ int gemm_pick_block_n(int M, int N) {
   return 256;
 }
 
+bool gemm_pick_quad(int M, int N, int K) {
+  (void)M;
+  (void)N;
+  (void)K;
+  static int env = -2;
+  if (env == -2) {
+    const char* e = std::getenv("SKY_GEMM_QUAD");
+    env = e ? std::atoi(e) : 0;
+  }
+  return env > 0;
+}
+
+bool gemm_pick_pair(int M, int N, int K) {
+  (void)N;
+  (void)K;
+  static int env = -2;
+  if (env == -2) {
+    const char* e = std::getenv("SKY_GEMM_PAIR");
+    env = e ? std::atoi(e) : -1;
+  }
+  if (env >= 0) return env != 0 && M > 128;
+  return false;  // measured: the TPC already merges the two SMs' identical B requests
+}
+
 int gemm_tiles_per_panel(int N, int block_n) { return (N + block_n - 1) / block_n; }
 
 namespace {
 static int g_num_sms = 0;
 
-template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32>
+// ---- stream-K workspace: one per (device, stream), because GEMMs on different streams overlap ----
+constexpr size_t kWsSlotBytes = static_cast<size_t>(BLOCK_M) * 256 * 4;  // one 128 x 256 fp32 tile
+constexpr int kWsMaxCtas = 160;                                          // >= SMs of the device
+constexpr int kWsMaxCtaTiles = 8192;
+struct StreamKWs {
+  float* ws = nullptr;
+  uint32_t* counters = nullptr;
+};
+std::mutex g_ws_mutex;
+std::map<std::pair<int, cudaStream_t>, StreamKWs> g_ws;
+
+// nullptr when the workspace does not exist yet and cannot be created (stream is capturing)
+const StreamKWs* get_ws(cudaStream_t stream) {
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  auto key = std::make_pair(dev_id, stream);
+  auto it = g_ws.find(key);
+  if (it != g_ws.end()) return &it->second;
+  cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  StreamKWs w;
+  if (cudaMalloc(&w.ws, 2 * kWsMaxCtas * kWsSlotBytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  if (cudaMalloc(&w.counters, 2 * kWsMaxCtaTiles * sizeof(uint32_t)) != cudaSuccess) {
+    cudaGetLastError();
+    cudaFree(w.ws);
+    return nullptr;
+  }
+  cudaMemset(w.counters, 0, 2 * kWsMaxCtaTiles * sizeof(uint32_t));
+  g_ws[key] = w;
+  return &g_ws[key];
+}
+
+// Stream-K pays when the classic schedule leaves SMs idle (few tiles) or ends on a ragged wave:
+// compare ceil(tiles / U) * nk against tiles * nk / U k-blocks per CTA (+ a fix-up allowance).
+bool want_stream_k(long long tiles, int nk, int units) {
+  static int env = -2;
+  if (env == -2) {
+    const char* e = std::getenv("SKY_GEMM_STREAMK");
+    env = e ? std::atoi(e) : -1;
+  }
+  if (env == 0) return false;
+  if (tiles <= 0 || nk < 8) return false;
+  const long long classic = (tiles + units - 1) / units * nk;
+  const long long streamed = (tiles * nk + units - 1) / units + 6;
+  if (streamed < 4) return false;
+  if (env == 1) return tiles % units != 0;
+  return streamed * 100 < classic * 85;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32, int CL>
 int launch_inst(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
-  using C = Cfg<BLOCK_N>;
+  constexpr bool PAIR = CL >= 2;
+  constexpr bool MC = CL == 4;
+  using C = Cfg<BLOCK_N, PAIR>;
   CUtensorMap tma, tmb;
   int rc;
   if (!A_MN)
-    rc = make_tmap_bf16_2d(&tma, a.A, a.K, a.M, a.lda, BLOCK_K, BLOCK_M);
+    rc = make_tmap_bf16_2d(&tma, a.A, a.K, a.M, a.lda, BLOCK_K, MC ? 64 : BLOCK_M);
   else
     rc = make_tmap_bf16_2d(&tma, a.A, a.M, a.K, a.lda, 64, BLOCK_K);
   if (rc) return rc;
   if (!B_MN)
-    rc = make_tmap_bf16_2d(&tmb, a.B, a.K, a.N, a.ldb, BLOCK_K, BLOCK_N);
+    rc = make_tmap_bf16_2d(&tmb, a.B, a.K, a.N, a.ldb, BLOCK_K, C::kBRows);
   else
     rc = make_tmap_bf16_2d(&tmb, a.B, a.N, a.K, a.ldb, 64, BLOCK_K);
   if (rc) return rc;
 
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, OUT_F32>;
+  GemmDev devp = dev;
+  {
+    if (g_num_sms == 0) {
+      int dev_id = 0;
+      cudaGetDevice(&dev_id);
+      cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev_id);
+    }
+    constexpr int UM = PAIR ? 2 * BLOCK_M : BLOCK_M;
+    const long long m_units = (a.M + UM - 1) / UM;
+    const long long n_blks = (a.N + BLOCK_N - 1) / BLOCK_N;
+    const long long tiles = m_units * (MC ? n_blks / 2 : n_blks);
+    const int nk = (a.K + BLOCK_K - 1) / BLOCK_K;
+    int units = g_num_sms / CL;
+    if (a.max_ctas > 0 && units > a.max_ctas / CL) units = a.max_ctas / CL;
+    if (units < 1) units = 1;
+    bool sk = a.stream_k < 0 ? want_stream_k(tiles, nk, units) : (a.stream_k != 0);
+    // every CTA must own at least 4 k-blocks, the CTA tiles must fit the counter array, a bias
+    // must not be added once per partial, and the grid must fit the workspace
+    if (tiles * nk < 4LL * units) sk = false;
+    if (m_units * (PAIR ? 2 : 1) * n_blks > kWsMaxCtaTiles || g_num_sms > kWsMaxCtas) sk = false;
+    if (a.accumulate && a.bias != nullptr) sk = false;
+    devp.stream_k = 0;
+    devp.ws = nullptr;
+    devp.counters = nullptr;
+    if (sk) {
+      if (a.accumulate) {
+        devp.stream_k = 1;  // partial sums go straight to the fp32 output with red.add
+      } else if (const StreamKWs* w = get_ws(stream)) {
+        devp.stream_k = 1;
+        devp.ws = w->ws;
+        devp.counters = w->counters;
+      }
+    }
+  }
+  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, OUT_F32, CL>;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e =
@@ -497,27 +855,33 @@ int launch_inst(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
     cudaGetDevice(&dev_id);
     cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev_id);
   }
-  const int num_tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BLOCK_N - 1) / BLOCK_N);
-  int grid = num_tiles < g_num_sms ? num_tiles : g_num_sms;
-  if (a.max_ctas > 0 && grid > a.max_ctas) grid = a.max_ctas;
-  cudaError_t le = launch_pdl(kern, dim3(grid), dim3(kNumThreads), C::kSmemBytes, stream, tma, tmb, dev);
+  constexpr int UNIT_M = PAIR ? 2 * BLOCK_M : BLOCK_M;
+  const int num_tiles =
+      ((a.M + UNIT_M - 1) / UNIT_M) * (((a.N + BLOCK_N - 1) / BLOCK_N) / (MC ? 2 : 1));
+  const int max_units = g_num_sms / CL;
+  int grid = (num_tiles < max_units && !devp.stream_k) ? num_tiles : max_units;
+  if (a.max_ctas > 0 && grid > a.max_ctas / CL) grid = a.max_ctas / CL;
+  if (grid < 1) grid = 1;
+  grid *= CL;
+  cudaError_t le = launch_pdl_cluster(kern, dim3(grid), dim3(kNumThreads), C::kSmemBytes, stream,
+                              CL, tma, tmb, devp);
   if (le != cudaSuccess) return static_cast<int>(le);
   return static_cast<int>(cudaGetLastError());
 }
 
-template <int BLOCK_N>
+template <int BLOCK_N, int PAIR>
 int dispatch_major(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
   if (!a.a_mn && !a.b_mn)
-    return a.out_f32 ? launch_inst<BLOCK_N, false, false, true>(a, dev, stream)
-                     : launch_inst<BLOCK_N, false, false, false>(a, dev, stream);
+    return a.out_f32 ? launch_inst<BLOCK_N, false, false, true, PAIR>(a, dev, stream)
+                     : launch_inst<BLOCK_N, false, false, false, PAIR>(a, dev, stream);
   if (!a.a_mn && a.b_mn)
-    return a.out_f32 ? launch_inst<BLOCK_N, false, true, true>(a, dev, stream)
-                     : launch_inst<BLOCK_N, false, true, false>(a, dev, stream);
+    return a.out_f32 ? launch_inst<BLOCK_N, false, true, true, PAIR>(a, dev, stream)
+                     : launch_inst<BLOCK_N, false, true, false, PAIR>(a, dev, stream);
   if (a.a_mn && a.b_mn)
-    return a.out_f32 ? launch_inst<BLOCK_N, true, true, true>(a, dev, stream)
-                     : launch_inst<BLOCK_N, true, true, false>(a, dev, stream);
-  return a.out_f32 ? launch_inst<BLOCK_N, true, false, true>(a, dev, stream)
-                   : launch_inst<BLOCK_N, true, false, false>(a, dev, stream);
+    return a.out_f32 ? launch_inst<BLOCK_N, true, true, true, PAIR>(a, dev, stream)
+                     : launch_inst<BLOCK_N, true, true, false, PAIR>(a, dev, stream);
+  return a.out_f32 ? launch_inst<BLOCK_N, true, false, true, PAIR>(a, dev, stream)
+                   : launch_inst<BLOCK_N, true, false, false, PAIR>(a, dev, stream);
 }
 }  // namespace
 
@@ -550,9 +914,26 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   d.wait_mult = a.wait_mult;
   d.error_flag = a.error_flag;
   d.debug = a.debug;
+  d.stream_k = 0;
+  d.ws = nullptr;
+  d.counters = nullptr;
   const int bn = a.block_n ? a.block_n : gemm_pick_block_n(a.M, a.N);
-  if (bn == 256) return dispatch_major<256>(a, d, stream);
-  if (bn == 128) return dispatch_major<128>(a, d, stream);
+  const bool pair = a.pair < 0 ? gemm_pick_pair(a.M, a.N, a.K) : (a.pair != 0);
+  if (pair) {
+    // two pairs + A multicast needs an even number of N tiles
+    const bool quad = (a.pair == 2 || (a.pair < 0 && gemm_pick_quad(a.M, a.N, a.K))) &&
+                      (((a.N + bn - 1) / bn) % 2 == 0);
+    if (quad) {
+      if (bn == 256) return dispatch_major<256, 4>(a, d, stream);
+      if (bn == 128) return dispatch_major<128, 4>(a, d, stream);
+      return 905;
+    }
+    if (bn == 256) return dispatch_major<256, 2>(a, d, stream);
+    if (bn == 128) return dispatch_major<128, 2>(a, d, stream);
+    return 905;
+  }
+  if (bn == 256) return dispatch_major<256, 1>(a, d, stream);
+  if (bn == 128) return dispatch_major<128, 1>(a, d, stream);
   return 905;
 }
 

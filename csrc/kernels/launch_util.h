@@ -3,7 +3,7 @@
 // and CTA scheduling overlap the tail of the previous kernel in the stream (also inside captured
 // CUDA graphs: CUDA >= 12.3 records programmatic edges).  The kernels call griddepcontrol.wait
 // before they touch any memory produced by earlier kernels, so ordering semantics are unchanged.
-// SKY_PDL=0 disables the attribute (A/B testing).
+// SKY_PDL=1 enables the attribute (measured +1.4 % at 1 GPU, -3 % at 2 GPUs => off by default).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -16,25 +16,39 @@ inline bool pdl_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = std::getenv("SKY_PDL");
-    v = (e != nullptr && e[0] == '0') ? 0 : 1;
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;  // measured: <= 1.5 % either way -> off by default
   }
   return v == 1;
 }
 
+// `cluster_x` > 1 launches thread-block clusters of that many CTAs along x (CTA pairs).
 template <class... KArgs, class... Args>
-inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                              cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_pdl_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                      cudaStream_t stream, int cluster_x, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (cluster_x > 1) {
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = static_cast<unsigned>(cluster_x);
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
+    cfg.numAttrs = 2;
+  }
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(std::forward<Args>(args))...);
+}
+
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  return launch_pdl_cluster(kern, grid, block, smem, stream, 1, std::forward<Args>(args)...);
 }
 
 }  // namespace sky

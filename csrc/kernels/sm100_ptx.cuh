@@ -134,6 +134,88 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // ----------------------------------------------------------------------------------------------
+// CTA pair (cta_group::2): two CTAs of a 2-cluster (same TPC) run ONE UMMA of M = 256.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile; the leader (cluster rank 0) issues the
+// MMAs, which read both CTAs' shared memory and write both CTAs' TMEM.  Halving the B bytes per
+// CTA is what takes the main loop off the L2 -> SM bandwidth limit (profiles/gemm_pair.md).
+// ----------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n"
+               "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cta address -> shared::cluster address of the same offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
+               : "memory");
+}
+// TMA load whose completion bytes land on a barrier that may live in the PEER CTA
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap,
+                                                 uint32_t bar_cluster_addr, int c_inner,
+                                                 int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+      "[%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(bar_cluster_addr), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+// same, multicast: the box lands at the same CTA-relative offset in every CTA of `mask`; the
+// completion bytes go to the barrier at `bar_addr`'s offset in each destination's pair leader
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem_dst, const CUtensorMap* tmap,
+                                                    uint32_t bar_addr, int c_inner, int c_outer,
+                                                    uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%4, %5}], [%2], %3;"
+      ::"r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(bar_addr), "h"(mask), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t* smem_dst, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "r"(ncols)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+               : "memory");
+}
+// commit: arrive on the barrier at this offset in BOTH CTAs of the pair once the MMAs retired
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 "
+      "[%0], %1;" ::"r"(smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a,
+                                                  uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// ----------------------------------------------------------------------------------------------
 // tcgen05: descriptors
 // ----------------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor, SWIZZLE_128B.  Bit layout (PTX ISA):

@@ -342,6 +342,18 @@ class BertSpanFn(torch.autograd.Function):
 # stage's last dgrad GEMM has published its tiles to the previous stage.
 _DEFER_WGRAD = [False]
 _WGRAD_QUEUE: list = []
+# "immediate" mode: every weight gradient is launched at once, but on a side stream that forks
+# from the current point of the main stream, so it overlaps the rest of the dgrad chain.
+_WGRAD_STREAM: list = [None]
+_WGRAD_KEEP: list = []
+
+
+def set_wgrad_stream(stream) -> None:
+    _WGRAD_STREAM[0] = stream
+
+
+def wgrad_keepalive() -> list:
+    return _WGRAD_KEEP
 
 
 def set_wgrad_deferral(on: bool) -> None:
@@ -350,18 +362,33 @@ def set_wgrad_deferral(on: bool) -> None:
         flush_wgrads()
 
 
-def flush_wgrads() -> None:
+def flush_wgrads() -> list:
+    """Launch every queued weight / bias gradient on the CURRENT stream; returns the queued
+    tensors so that a caller that flushed onto a side stream can keep them alive until it joins."""
     q = list(_WGRAD_QUEUE)
     _WGRAD_QUEUE.clear()
     for g, act, wbank, bbank in q:
         nat.gemm(g, act, a_mn=True, b_mn=True, out=wbank.grad(), accumulate=True)
         nat.colsum_(g, bbank.grad())
+    return q
+
+
+def pending_wgrads() -> int:
+    return len(_WGRAD_QUEUE)
 
 
 def _wgrad(g: torch.Tensor, act: torch.Tensor, wbank: ParamBank, bbank: ParamBank) -> None:
     """dW += g^T act (both operands MN-major over the token dimension), db += colsum(g)."""
     if _DEFER_WGRAD[0]:
         _WGRAD_QUEUE.append((g, act, wbank, bbank))
+        return
+    side = _WGRAD_STREAM[0]
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream(g.device))
+        with torch.cuda.stream(side):
+            nat.gemm(g, act, a_mn=True, b_mn=True, out=wbank.grad(), accumulate=True)
+            nat.colsum_(g, bbank.grad())
+        _WGRAD_KEEP.append((g, act))
         return
     nat.gemm(g, act, a_mn=True, b_mn=True, out=wbank.grad(), accumulate=True)
     nat.colsum_(g, bbank.grad())

@@ -151,6 +151,8 @@ def gemm(
     wait_mult: int = 0,
     error_flag: int = 0,
     block_n: int = 0,
+    pair: int = -1,
+    stream_k: int = -1,
     max_ctas: int = 0,
     debug: int = 0,
 ) -> Optional[torch.Tensor]:
@@ -196,7 +198,7 @@ def gemm(
         aux=_ptr(aux), ldaux=0 if aux is None else aux.stride(0), act=act, add_aux=add_aux,
         dropout_p=float(dropout_p), rng_state=0 if rng is None else rng.ptr,
         rng_stream=rng_stream, signal_flags=signal_flags, wait_flags=wait_flags,
-        wait_epoch=wait_epoch, wait_mult=wait_mult, error_flag=error_flag, block_n=block_n,
+        wait_epoch=wait_epoch, wait_mult=wait_mult, error_flag=error_flag, block_n=block_n, pair=pair, stream_k=stream_k,
         max_ctas=max_ctas, debug=debug, stream=_stream(),
     )
     return out

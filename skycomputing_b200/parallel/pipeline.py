@@ -87,6 +87,22 @@ class PipelineEngine:
         self.stage.engine_managed_backward = True
         self.launches_per_step = 0
         self._defer_wgrad = False
+        self._wgrad_stream = None
+        self._wgrad_forked = False
+        self._wgrad_keepalive: list = []
+        import os as _os
+
+        # inline | lazy (queue, flush in front of the next backward) | lazy_stream (same, on a side
+        # stream) | immediate (side stream, forked at the producing kernel) | auto
+        self._wgrad_mode = _os.environ.get("SKY_WGRAD", "auto")
+        self._wgrad_side_stream_enabled = False
+        self._wgrad_immediate = False
+        # device-side timeline (SKY_TRACE=1 or enable_trace()): one %globaltimer stamp in front of
+        # and behind every F / B / W / optimizer phase, written by 1-thread kernels so that the
+        # stamps survive CUDA-graph capture
+        self._trace = _os.environ.get("SKY_TRACE", "0") == "1"
+        self._trace_buf: Optional[torch.Tensor] = None
+        self._trace_tags: list = []
 
     # ------------------------------------------------------------------ setup
     def _native_active(self) -> bool:
@@ -153,11 +169,20 @@ class PipelineEngine:
             # device timers cannot be recorded inside a captured graph
             self.stage._record_forward_time = False
             self.stage._logger = None
-        if multi and self._native_active():
-            from ..ops.functions import set_wgrad_deferral
+        if self._native_active():
+            from ..ops.functions import set_wgrad_deferral, set_wgrad_stream
 
-            self._defer_wgrad = True
-            set_wgrad_deferral(True)
+            mode = self._wgrad_mode
+            if mode == "auto":
+                mode = "lazy_stream" if multi else "immediate"  # measured best (profiles/bench_history.md)
+            if mode in ("lazy", "lazy_stream") and multi:
+                self._defer_wgrad = True
+                self._wgrad_side_stream_enabled = mode == "lazy_stream"
+                set_wgrad_deferral(True)
+            elif mode in ("immediate", "lazy_stream"):
+                self._wgrad_stream = torch.cuda.Stream(device=self.device)
+                self._wgrad_immediate = True
+                set_wgrad_stream(self._wgrad_stream)
         self._order = (one_f_one_b_order if self.schedule == "1f1b" else sequential_order)(
             self.s, self.P, self.m)
         self._setup_done = True
@@ -196,7 +221,9 @@ class PipelineEngine:
         if self.out_fused and not self.is_first:
             # the mask travels with the activation (own flag); relay it as early as possible
             self.fused.next.send_mask(args[-1], j)
+        self._mark(("F", j, "begin"))
         outs = st(*args)
+        self._mark(("F", j, "end"))
         if self.out_fused and self.is_first:
             self.fused.next.send_mask(outs[-1], j)  # produced by the embeddings of this stage
         loss = None
@@ -216,6 +243,7 @@ class PipelineEngine:
         # what would otherwise be pipeline bubble, and they never delay the input gradient that
         # the previous stage is waiting for.
         self._flush_wgrads()
+        self._mark(("B", j, "begin"))
         st.begin_backward()
         if self.is_last:
             loss.backward()
@@ -230,15 +258,76 @@ class PipelineEngine:
                     gs.append(g.to(o.dtype))
             torch.autograd.backward(ts, gs)
         st.end_backward()
+        self._mark(("B", j, "end"))
         if self.is_first or self.in_fused:
             return None
         return self._in_grads(args)
 
     def _flush_wgrads(self) -> None:
-        if self._defer_wgrad:
-            from ..ops.functions import flush_wgrads
+        """Launch the queued weight gradients.  They are independent of the input-gradient chain,
+        so they go to a side stream and run CONCURRENTLY with the next micro-batch's kernels
+        (most of which are single-wave GEMMs that leave SMs idle); the side stream is forked from
+        / joined to the main stream with events, which CUDA-graph capture records as parallel
+        branches."""
+        if not self._defer_wgrad:
+            return
+        from ..ops.functions import flush_wgrads, pending_wgrads
 
+        if pending_wgrads() == 0:
+            return
+        if not self._wgrad_side_stream_enabled:
+            self._mark(("W", -1, "begin"))
             flush_wgrads()
+            self._mark(("W", -1, "end"))
+            return
+        if self._wgrad_stream is None:
+            self._wgrad_stream = torch.cuda.Stream(device=self.device)
+        main = torch.cuda.current_stream(self.device)
+        self._wgrad_stream.wait_stream(main)
+        with torch.cuda.stream(self._wgrad_stream):
+            self._mark(("W", -1, "begin"))
+            self._wgrad_keepalive.extend(flush_wgrads())
+            self._mark(("W", -1, "end"))
+        self._wgrad_forked = True
+
+    def _join_wgrads(self) -> None:
+        if self._wgrad_immediate:
+            from ..ops.functions import wgrad_keepalive
+
+            torch.cuda.current_stream(self.device).wait_stream(self._wgrad_stream)
+            wgrad_keepalive().clear()
+            return
+        if self._wgrad_forked:
+            torch.cuda.current_stream(self.device).wait_stream(self._wgrad_stream)
+            self._wgrad_forked = False
+        self._wgrad_keepalive.clear()
+
+    # ------------------------------------------------------------------ device timeline
+    def enable_trace(self) -> None:
+        assert self._graph is None, "enable_trace() must precede CUDA-graph capture"
+        self._trace = True
+
+    def _mark(self, tag) -> None:
+        if not self._trace or self.device.type != "cuda":
+            return
+        from ..ops import native as nat
+
+        if self._trace_buf is None:
+            self._trace_buf = torch.zeros(8 * (2 * self.m + 4) + 64, dtype=torch.int64, device=self.device)
+        i = len(self._trace_tags)
+        if i >= self._trace_buf.numel():
+            return
+        self._trace_tags.append(tag)
+        nat.ext().record_time(self._trace_buf.data_ptr() + 8 * i,
+                              torch.cuda.current_stream(self.device).cuda_stream)
+
+    def trace(self) -> list:
+        """[(tag, ns)] of the LAST executed step: tags are ('F'|'B'|'W'|'OPT', j, 'begin'|'end')."""
+        if self._trace_buf is None:
+            return []
+        torch.cuda.synchronize(self.device)
+        t = self._trace_buf.cpu().tolist()
+        return [(tag, t[i]) for i, tag in enumerate(self._trace_tags)]
 
     # ------------------------------------------------------------------ comm helpers (unfused)
     @staticmethod
@@ -309,6 +398,8 @@ class PipelineEngine:
         if self._advance_rng and self._native_active():
             advance_rng()
         self._loss_acc.zero_()
+        self._trace_tags = []
+        self._mark(("STEP", 0, "begin"))
         chunks = [t.chunk(self.m, dim=0) for t in inputs] if self.is_first else None
         label_chunks = labels.chunk(self.m, dim=0) if (self.is_last and labels is not None) else None
         need_recv_f = not self.is_first and not self.in_fused
@@ -347,7 +438,10 @@ class PipelineEngine:
                     else:
                         self._send_backward(in_grads)
         self._flush_wgrads()
+        self._join_wgrads()
+        self._mark(("OPT", 0, "begin"))
         self.optimizer.step()
+        self._mark(("OPT", 0, "end"))
         if self.comm is not None:
             self.comm.wait(self._pending_sends)
             self._pending_sends = []

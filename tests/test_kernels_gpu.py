@@ -238,3 +238,44 @@ def test_gemm_flag_handshake_single_gpu(nat):
     assert flags.tolist() == [tiles] * (M // 128)
     ref_mid = (x.float() @ w1.float().t()).to(torch.bfloat16)
     _close(out, ref_mid.float() @ w2.float().t(), atol=0.1)
+
+
+@pytest.mark.parametrize("pair,stream_k", [(1, 0), (0, 1), (1, 1), (2, 0), (2, 1)])
+@pytest.mark.parametrize("M,N,K", [(2048, 1024, 4096), (1000, 520, 1096), (4096, 1024, 1024)])
+def test_gemm_pair_and_stream_k_schedules(nat, M, N, K, pair, stream_k):
+    """cta_group::2 CTA pairs and the stream-K schedule (split tiles reduced through the
+    workspace by the last-arriving CTA) must match the classic schedule bit-for-bit in layout and
+    closely in value; run twice so the second launch sees the counters the first one left."""
+    torch.manual_seed(11)
+    a, b = _rand(M, K), _rand(N, K)
+    bias = torch.randn(N, device="cuda")
+    ref = a.float() @ b.float().t() + bias
+    for block_n in (128, 256):
+        for _ in range(2):
+            out = nat.gemm(a, b, bias=bias, block_n=block_n, pair=pair, stream_k=stream_k)
+            _close(out, ref, atol=0.05 * math.sqrt(K) / 8)
+    # dgrad / wgrad operand layouts
+    dy = _rand(M, N)
+    dx = nat.gemm(dy, b, b_mn=True, pair=pair, stream_k=stream_k)
+    _close(dx, dy.float() @ b.float(), atol=0.05 * math.sqrt(N) / 8)
+    if M % 8 == 0:
+        dw = torch.zeros(N, K, device="cuda", dtype=torch.float32)
+        for _ in range(2):
+            nat.gemm(dy, a, a_mn=True, b_mn=True, out=dw, accumulate=True, pair=pair, stream_k=stream_k)
+        _close(dw, 2 * (dy.float().t() @ a.float()), atol=0.05 * math.sqrt(M) / 4)
+
+
+def test_gemm_stream_k_fused_epilogue(nat):
+    """GELU + second output + residual paths on a split tile (only the finishing CTA applies them)."""
+    torch.manual_seed(12)
+    M, N, K = 512, 512, 2048
+    a, b = _rand(M, K), _rand(N, K, scale=0.05)
+    bias = torch.randn(N, device="cuda") * 0.1
+    pre = torch.empty(M, N, dtype=torch.bfloat16, device="cuda")
+    out = nat.gemm(a, b, bias=bias, act=nat.ACT_GELU, out2=pre, stream_k=1)
+    h = a.float() @ b.float().t() + bias
+    _close(pre, h)
+    _close(out, h * 0.5 * (1.0 + torch.erf(h / math.sqrt(2.0))))
+    res = _rand(M, N)
+    out = nat.gemm(a, b, bias=bias, aux=res, add_aux=True, stream_k=1, pair=1)
+    _close(out, h + res.float())

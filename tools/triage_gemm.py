@@ -11,17 +11,39 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from skycomputing_b200.ops import native as nat  # noqa: E402
 
 
+_SIDE = None
+
+
 def timeit(fn, iters=20, warmup=5):
-    for _ in range(warmup):
-        fn()
+    """Time `fn` as `iters` back-to-back launches replayed from a CUDA graph: host launch cost
+    (tensor-map encode + pybind, ~14 us per call) would otherwise hide every kernel shorter than
+    that."""
+    global _SIDE
+    if _SIDE is None:
+        _SIDE = torch.cuda.Stream()
+    side = _SIDE
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        # warm up ON the capture stream: per-stream resources (the stream-K workspace) cannot be
+        # created while the stream is capturing
+        for _ in range(warmup):
+            fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            for _ in range(iters):
+                fn()
+    torch.cuda.synchronize()
+    g.replay()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(iters):
-        fn()
+    for _ in range(3):
+        g.replay()
     e1.record()
     torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters
+    return e0.elapsed_time(e1) / (3 * iters)
 
 
 def main():
