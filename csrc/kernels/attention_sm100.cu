@@ -74,7 +74,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnDev
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // uniform: MMA operands stay in URs
   const int bh = blockIdx.x;
   const int b = bh / p.heads;
   const int h = bh % p.heads;
@@ -98,7 +98,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnDev
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one_sync()) {
     mbar_expect_tx(&bars[0], 3 * kTile);
     tma_load_2d(sQ, &tmap_qkv, &bars[0], h * kD, b * kS);
     tma_load_2d(sK, &tmap_qkv, &bars[0], p.H + h * kD, b * kS);
@@ -173,7 +173,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnDev
   tcgen05_fence_before();
   __syncthreads();
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one_sync()) {
     tcgen05_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16_f32(128, 64, false, true);
 #pragma unroll
@@ -238,7 +238,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 3);
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int bh = blockIdx.x;
   const int b = bh / p.heads;
   const int h = bh % p.heads;
@@ -265,7 +265,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   // S and dP are dead after the softmax phase: the three output accumulators re-use their columns
   constexpr uint32_t cS = 0, cdP = 128, cdV = 0, cdK = 64, cdQ = 128;
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one_sync()) {
     mbar_expect_tx(&bars[0], 4 * kTile);
     tma_load_2d(sQ, &tmap_qkv, &bars[0], h * kD, b * kS);
     tma_load_2d(sK, &tmap_qkv, &bars[0], p.H + h * kD, b * kS);
@@ -377,7 +377,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
   tcgen05_fence_before();
   __syncthreads();
 
-  if (tid == 0) {
+  if (warp == 0 && elect_one_sync()) {
     tcgen05_fence_after();
     // dV[key, d] = sum_q P[q,key] dO[q,d] : A = P (MN-major, 2 key-chunks 16KB apart), B = dO (MN)
     // dK[key, d] = sum_q dS[q,key] Q[q,d] : A = dS (MN-major),                         B = Q  (MN)

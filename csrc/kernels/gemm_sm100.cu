@@ -140,7 +140,9 @@ struct Sched {
 // on the same 256 rows and neighbouring N tiles and MULTICAST the A operand to each other (each
 // CTA fetches half of its 128 A rows from L2 and TMA delivers them to itself and to the CTA of
 // the other pair that needs the same rows).
-template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32, int CL>
+// SK = stream-K schedule compiled in (a separate instantiation: its bookkeeping costs registers in
+// the epilogue, which the classic kernels - the ones every training step runs - must not pay).
+template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32, int CL, bool SK>
 __global__ void __launch_bounds__(kNumThreads, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
                     const __grid_constant__ CUtensorMap tmap_b, const GemmDev p) {
@@ -168,7 +170,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
   float* s_bias = reinterpret_cast<float*>(smem + kStages * C::kStageBytes + 256);
 
-  const int warp_idx = threadIdx.x >> 5;
+  // warp-uniform by construction AND visibly so to the compiler: the producer / MMA warps run
+  // converged with one ELECTED lane issuing, so that TMA / UMMA operands stay in uniform
+  // registers.  (A single-lane `if (lane == 0)` role costs an ELECT + 5 R2UR.BROADCAST in front
+  // of every UTCHMMA: measured 175 cycles per MMA instead of 64-128, profiles/gemm_schedules.md.)
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
 
   // tile scheduler: a "unit" is one CTA (128 rows) or one CTA pair (256 rows)
@@ -222,7 +228,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   pdl_wait();
   pdl_launch_dependents();
 
-  if (warp_idx == 0 && lane == 0) {
+  if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
     int stage = 0;
     uint32_t phase = 0;
@@ -233,7 +239,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     const uint32_t full_mc0 = smem_u32(&full_bar[0]) & 0xFEFFFFFFu;
     const uint16_t mc_mask = static_cast<uint16_t>((1u << cl_rank) | (1u << (cl_rank ^ 2u)));
     Sched sched;
-    sched.init(p.stream_k, unit_id, num_units, num_tiles, num_k_blks);
+    sched.init(SK ? 1 : 0, unit_id, num_units, num_tiles, num_k_blks);
     Work w;
     while (sched.next(w)) {
       const int tile = w.tile;
@@ -241,22 +247,27 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       const int n_blk = (tile / num_m_units) * (MC ? 2 : 1) + (MC ? static_cast<int>(pair_idx) : 0);
       const int b_row0 = n_blk * BLOCK_N + static_cast<int>(cta_rank) * C::kBRows;
       if (p.wait_flags != nullptr && m_blk * BLOCK_M < p.M) {
-        const uint32_t target = (*p.wait_epoch) * p.wait_mult;
-        if (!wait_flag_ge(p.wait_flags + m_blk, target, kFlagTimeoutNs)) {
-          if (p.error_flag) atomicExch(p.error_flag, 1);
+        if (elect_one_sync()) {
+          const uint32_t target = (*p.wait_epoch) * p.wait_mult;
+          if (!wait_flag_ge(p.wait_flags + m_blk, target, kFlagTimeoutNs)) {
+            if (p.error_flag) atomicExch(p.error_flag, 1);
+          }
+          fence_proxy_async();  // peer generic-proxy writes -> our async-proxy (TMA) reads
         }
-        fence_proxy_async();  // peer generic-proxy writes -> our async-proxy (TMA) reads
+        __syncwarp();
       }
       for (int kb = w.kb0; kb < w.kb1; ++kb) {
         mbar_wait(&empty_bar[stage], phase ^ 1);
         if (!PAIR && p.debug == 3) {  // triage: no loads at all, the MMAs chew on stale smem
-          mbar_arrive(&full_bar[stage]);
+          if (elect_one_sync()) mbar_arrive(&full_bar[stage]);
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
           continue;
         }
+        if (elect_one_sync()) {
         if (leader) mbar_expect_tx(&full_bar[stage], (PAIR ? 2 : 1) * C::kStageBytes);
         uint8_t* sa = smem_a + stage * C::kABytes;
         uint8_t* sb = smem_b + stage * C::kBBytes;
@@ -289,13 +300,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           for (int c = 0; c < C::kBRows / 64; ++c)
             load(sb + c * (BLOCK_K * 128), &tmap_b, b_row0 + c * 64, kb * BLOCK_K);
         }
+        }  // elected lane
+        __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
         }
       }
     }
-  } else if (warp_idx == 1 && lane == 0 && leader) {
+  } else if (warp_idx == 1 && leader) {
     // ===================================== MMA issuer ======================================
     constexpr uint32_t idesc = make_idesc_bf16_f32(UNIT_M, BLOCK_N, A_MN, B_MN);
     // K-major  SW128: 8-row atoms 1024B apart (SBO), LBO unused (1); K advance = 32B per UMMA_K
@@ -309,7 +322,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
     uint32_t phase = 0;
     int it = 0;
     Sched sched;
-    sched.init(p.stream_k, unit_id, num_units, num_tiles, num_k_blks);
+    sched.init(SK ? 1 : 0, unit_id, num_units, num_tiles, num_k_blks);
     Work w;
     for (; sched.next(w); ++it) {
       const int acc = it & 1;
@@ -321,14 +334,18 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         mbar_wait(&full_bar[stage], phase);
         tcgen05_fence_after();
         if (!PAIR && p.debug == 4) {  // triage: loads only, no MMA
-          mbar_arrive(&empty_bar[stage]);
-          if (kb == w.kb1 - 1) mbar_arrive(&tmem_full_bar[acc]);
+          if (elect_one_sync()) {
+            mbar_arrive(&empty_bar[stage]);
+            if (kb == w.kb1 - 1) mbar_arrive(&tmem_full_bar[acc]);
+          }
+          __syncwarp();
           if (++stage == kStages) {
             stage = 0;
             phase ^= 1;
           }
           continue;
         }
+        if (elect_one_sync()) {
         const uint64_t desc_a =
             make_smem_desc_sw128(smem_u32(smem_a + stage * C::kABytes), a_lbo, 1024);
         const uint64_t desc_b =
@@ -351,6 +368,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
           umma_commit(&empty_bar[stage]);
           if (kb == w.kb1 - 1) umma_commit(&tmem_full_bar[acc]);
         }
+        }  // elected lane
+        __syncwarp();
         if (++stage == kStages) {
           stage = 0;
           phase ^= 1;
@@ -390,7 +409,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         PAIR ? mapa_shared(smem_u32(&tmem_empty_bar[0]), leader_rank)
              : smem_u32(&tmem_empty_bar[0]);
     Sched sched;
-    sched.init(p.stream_k, unit_id, num_units, num_tiles, num_k_blks);
+    sched.init(SK ? 1 : 0, unit_id, num_units, num_tiles, num_k_blks);
     Work w;
     uint32_t* s_ticket = tmem_ptr_smem + 1;
     constexpr int kCtasPerUnit = CL;
@@ -437,7 +456,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       bool finisher = true;
       int n_contrib = 1, u_first = 0;
       float* ws_mine = nullptr;
-      const bool partial = p.stream_k && !(w.kb0 == 0 && w.kb1 == num_k_blks) && !p.accumulate;
+      const bool partial = SK && !(w.kb0 == 0 && w.kb1 == num_k_blks) && !p.accumulate;
       const int ctile = n_blk * (num_m_units * (PAIR ? 2 : 1)) + m_blk;
       if (partial) {
         u_first = sched.unit_of(static_cast<long long>(tile) * num_k_blks);
@@ -775,7 +794,7 @@ const StreamKWs* get_ws(cudaStream_t stream) {
 
 // Stream-K pays when the classic schedule leaves SMs idle (few tiles) or ends on a ragged wave:
 // compare ceil(tiles / U) * nk against tiles * nk / U k-blocks per CTA (+ a fix-up allowance).
-bool want_stream_k(long long tiles, int nk, int units) {
+bool want_stream_k(long long tiles, int nk, int units, bool accumulate) {
   static int env = -2;
   if (env == -2) {
     const char* e = std::getenv("SKY_GEMM_STREAMK");
@@ -787,7 +806,15 @@ bool want_stream_k(long long tiles, int nk, int units) {
   const long long streamed = (tiles * nk + units - 1) / units + 6;
   if (streamed < 4) return false;
   if (env == 1) return tiles % units != 0;
-  return streamed * 100 < classic * 85;
+  // Measured (profiles/gemm_schedules.md): the fix-up of split tiles (park + re-read 128 KB per
+  // CTA, finisher wait) costs more than the idle SMs it recovers on every BERT shape, and with
+  // >= units/2 tiles the chip-wide L2 -> SM rate is the limit anyway.  It pays for fp32 `+=`
+  // outputs (weight gradients: partials are red.add'ed, no fix-up) with few tiles and a deep K.
+  // ... in isolation (attn_out wgrad 27 -> 17 us).  Inside the training step those weight
+  // gradients run on the side stream NEXT TO the dgrad chain, where a 148-CTA stream-K grid takes
+  // SMs away from the critical path: 12.62 ms/step with it, 12.50 ms without => opt-in only.
+  (void)accumulate;
+  return false;
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, bool OUT_F32, int CL>
@@ -823,7 +850,7 @@ int launch_inst(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
     int units = g_num_sms / CL;
     if (a.max_ctas > 0 && units > a.max_ctas / CL) units = a.max_ctas / CL;
     if (units < 1) units = 1;
-    bool sk = a.stream_k < 0 ? want_stream_k(tiles, nk, units) : (a.stream_k != 0);
+    bool sk = a.stream_k < 0 ? want_stream_k(tiles, nk, units, a.accumulate) : (a.stream_k != 0);
     // every CTA must own at least 4 k-blocks, the CTA tiles must fit the counter array, a bias
     // must not be added once per partial, and the grid must fit the workspace
     if (tiles * nk < 4LL * units) sk = false;
@@ -842,13 +869,19 @@ int launch_inst(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
       }
     }
   }
-  auto kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, OUT_F32, CL>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  // stream-K instantiations exist for independent CTAs only (pairs / clusters did not profit)
+  if (CL != 1) devp.stream_k = 0;
+  void (*kern)(CUtensorMap, CUtensorMap, GemmDev) =
+      gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, OUT_F32, CL, false>;
+  if constexpr (CL == 1) {
+    if (devp.stream_k) kern = gemm_tcgen05_kernel<BLOCK_N, A_MN, B_MN, OUT_F32, CL, true>;
+  }
+  static bool attr_set[2] = {false, false};
+  if (!attr_set[devp.stream_k ? 1 : 0]) {
     cudaError_t e =
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes);
     if (e != cudaSuccess) return static_cast<int>(e);
-    attr_set = true;
+    attr_set[devp.stream_k ? 1 : 0] = true;
   }
   if (g_num_sms == 0) {
     int dev_id = 0;

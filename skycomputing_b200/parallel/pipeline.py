@@ -90,6 +90,7 @@ class PipelineEngine:
         self._wgrad_stream = None
         self._wgrad_forked = False
         self._wgrad_keepalive: list = []
+        self._wgrad_tslot: Optional[torch.Tensor] = None
         import os as _os
 
         # inline | lazy (queue, flush in front of the next backward) | lazy_stream (same, on a side
@@ -101,6 +102,7 @@ class PipelineEngine:
         # and behind every F / B / W / optimizer phase, written by 1-thread kernels so that the
         # stamps survive CUDA-graph capture
         self._trace = _os.environ.get("SKY_TRACE", "0") == "1"
+        self._nvtx = _os.environ.get("SKY_NVTX", "0") == "1"
         self._trace_buf: Optional[torch.Tensor] = None
         self._trace_tags: list = []
 
@@ -284,9 +286,21 @@ class PipelineEngine:
             self._wgrad_stream = torch.cuda.Stream(device=self.device)
         main = torch.cuda.current_stream(self.device)
         self._wgrad_stream.wait_stream(main)
+        slow = float(getattr(self.stage, "_slowdown", 0) or 0)
         with torch.cuda.stream(self._wgrad_stream):
             self._mark(("W", -1, "begin"))
+            if slow > 0:
+                # a simulated slow device is slow for its weight gradients too (own time slot: the
+                # stage's forward/backward throttle may be running on the main stream right now)
+                from ..ops import native as nat
+
+                if self._wgrad_tslot is None:
+                    self._wgrad_tslot = torch.zeros(1, dtype=torch.int64, device=self.device)
+                side = self._wgrad_stream.cuda_stream
+                nat.ext().record_time(self._wgrad_tslot.data_ptr(), side)
             self._wgrad_keepalive.extend(flush_wgrads())
+            if slow > 0:
+                nat.ext().spin_factor(self._wgrad_tslot.data_ptr(), slow, side)
             self._mark(("W", -1, "end"))
         self._wgrad_forked = True
 
@@ -308,6 +322,12 @@ class PipelineEngine:
         self._trace = True
 
     def _mark(self, tag) -> None:
+        if self._nvtx and self.device.type == "cuda":
+            # NVTX ranges for nsys / ncu --nvtx (host-side: they bracket the LAUNCHES of a phase)
+            if tag[2] == "begin":
+                torch.cuda.nvtx.range_push(f"{tag[0]}{tag[1]}")
+            else:
+                torch.cuda.nvtx.range_pop()
         if not self._trace or self.device.type != "cuda":
             return
         from ..ops import native as nat
