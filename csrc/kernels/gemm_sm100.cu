@@ -725,15 +725,17 @@ int gemm_pick_block_n(int M, int N) {
 }
 
 bool gemm_pick_quad(int M, int N, int K) {
-  (void)M;
-  (void)N;
-  (void)K;
+  // Two cta_group::2 pairs per cluster with the A operand multicast between them.  Measured
+  // (profiles/gemm_schedules.md): wins 20-25 % on the few-tile, deep-K shapes that pick 128-wide
+  // tiles (dgrads / FFN2 at <= 2048 tokens, attn_out wgrad), loses on everything else.
   static int env = -2;
   if (env == -2) {
     const char* e = std::getenv("SKY_GEMM_QUAD");
-    env = e ? std::atoi(e) : 0;
+    env = e ? std::atoi(e) : -1;
   }
-  return env > 0;
+  if (env == 0) return false;
+  if (env > 0) return true;
+  return M >= 256 && K >= 2048 && gemm_pick_block_n(M, N) == 128 && ((N + 127) / 128) % 2 == 0;
 }
 
 bool gemm_pick_pair(int M, int N, int K) {
@@ -951,10 +953,11 @@ int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   d.ws = nullptr;
   d.counters = nullptr;
   const int bn = a.block_n ? a.block_n : gemm_pick_block_n(a.M, a.N);
-  const bool pair = a.pair < 0 ? gemm_pick_pair(a.M, a.N, a.K) : (a.pair != 0);
+  const bool auto_quad = a.pair < 0 && a.block_n == 0 && gemm_pick_quad(a.M, a.N, a.K);
+  const bool pair = a.pair < 0 ? (auto_quad || gemm_pick_pair(a.M, a.N, a.K)) : (a.pair != 0);
   if (pair) {
     // two pairs + A multicast needs an even number of N tiles
-    const bool quad = (a.pair == 2 || (a.pair < 0 && gemm_pick_quad(a.M, a.N, a.K))) &&
+    const bool quad = (a.pair == 2 || auto_quad) &&
                       (((a.N + bn - 1) / bn) % 2 == 0);
     if (quad) {
       if (bn == 256) return dispatch_major<256, 4>(a, d, stream);
