@@ -136,8 +136,8 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 // ----------------------------------------------------------------------------------------------
 // CTA pair (cta_group::2): two CTAs of a 2-cluster (same TPC) run ONE UMMA of M = 256.  Each CTA
 // stages its own 128 rows of A and HALF of the B tile; the leader (cluster rank 0) issues the
-// MMAs, which read both CTAs' shared memory and write both CTAs' TMEM.  Halving the B bytes per
-// CTA is what takes the main loop off the L2 -> SM bandwidth limit (profiles/gemm_pair.md).
+// MMAs, which read both CTAs' shared memory and write both CTAs' TMEM.  This cuts the bytes each
+// CTA pulls from L2 by a third; measured effect and when it pays: profiles/gemm_schedules.md.
 // ----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
