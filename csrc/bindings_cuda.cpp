@@ -378,6 +378,14 @@ PYBIND11_MODULE(_cuda, m) {
         py::arg("dropout_p") = 0.f, py::arg("rng_state") = 0, py::arg("rng_stream") = 0,
         py::arg("wait_flags") = 0, py::arg("wait_epoch") = 0, py::arg("wait_mult") = 0,
         py::arg("error_flag") = 0, py::arg("stream") = 0);
+  m.def("ln_param_grad", [](uintptr_t dy, uintptr_t z, uintptr_t mean, uintptr_t rstd,
+                            uintptr_t dgamma, uintptr_t dbeta, int M, int H, uintptr_t stream) {
+    check(sky::launch_ln_param_grad(P<void>(dy), P<void>(z), P<const float>(mean),
+                                    P<const float>(rstd), P<float>(dgamma), P<float>(dbeta), M, H,
+                                    S(stream)),
+          "ln_param_grad");
+  }, py::arg("dy"), py::arg("z"), py::arg("mean"), py::arg("rstd"), py::arg("dgamma"),
+        py::arg("dbeta"), py::arg("M"), py::arg("H"), py::arg("stream") = 0);
   m.def("colsum", &colsum, py::arg("x"), py::arg("M"), py::arg("N"), py::arg("ldx"),
         py::arg("out"), py::arg("stream") = 0);
   m.def("attention_fwd", &attention_fwd, py::arg("qkv"), py::arg("mask"), py::arg("ctx"),

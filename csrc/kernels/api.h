@@ -104,6 +104,8 @@ struct LayerNormBwdArgs {
   int* error_flag = nullptr;
 };
 int launch_layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t stream);
+int launch_ln_param_grad(const void* dy, const void* z, const float* mean, const float* rstd,
+                         float* dgamma, float* dbeta, int M, int H, cudaStream_t stream);
 
 // y[i] = g[i] * gelu'(h[i])  (bf16, n % 8 == 0): only used when a stage cut separates FFN1 | FFN2
 int launch_dgelu_mul(const void* g, const void* h, void* y, long long n, cudaStream_t stream);

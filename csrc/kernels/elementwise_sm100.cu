@@ -886,17 +886,25 @@ int launch_layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t stream) {
 #undef SKY_LN_BWD
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return static_cast<int>(e);
-  if (a.dgamma != nullptr || a.dbeta != nullptr) {
-    dim3 g2((a.H + 255) / 256, 1);
-    int ry = (a.M + 63) / 64;
-    if (ry > 64) ry = 64;
-    if (ry < 1) ry = 1;
-    g2.y = ry;
-    // NOTE: when gated on peer flags, the row kernel above has already waited for every panel.
-    launch_pdl(ln_param_grad_kernel, g2, dim3(256), 0, stream, reinterpret_cast<const __nv_bfloat16*>(a.dy),
-                                                 reinterpret_cast<const __nv_bfloat16*>(a.z),
-                                                 a.mean, a.rstd, a.dgamma, a.dbeta, a.M, a.H);
-  }
+  // NOTE: when gated on peer flags, the row kernel above has already waited for every panel.
+  if (a.dgamma != nullptr || a.dbeta != nullptr)
+    return launch_ln_param_grad(a.dy, a.z, a.mean, a.rstd, a.dgamma, a.dbeta, a.M, a.H, stream);
+  SKY_LAUNCH_CHECK();
+}
+
+// dgamma += sum_rows dy * xhat, dbeta += sum_rows dy.  A separate entry point so that the engine
+// can take it off the input-gradient critical path (it is queued with the weight gradients).
+int launch_ln_param_grad(const void* dy, const void* z, const float* mean, const float* rstd,
+                         float* dgamma, float* dbeta, int M, int H, cudaStream_t stream) {
+  if (M <= 0) return 0;
+  dim3 g2((H + 255) / 256, 1);
+  int ry = (M + 63) / 64;
+  if (ry > 64) ry = 64;
+  if (ry < 1) ry = 1;
+  g2.y = ry;
+  launch_pdl(ln_param_grad_kernel, g2, dim3(256), 0, stream,
+             reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(z),
+             mean, rstd, dgamma, dbeta, M, H);
   SKY_LAUNCH_CHECK();
 }
 

@@ -276,8 +276,9 @@ class BertSpanFn(torch.autograd.Function):
             else:
                 dy2 = _flat2d(grads[0]).contiguous()
             dz2, dz2d = nat.layernorm_bwd(dy2, sv["z2"], sv["mean2"], sv["rstd2"], sp.g2.master(),
-                                          sp.g2.grad(), sp.b2n.grad(), dropout_p=p_hid, rng=rng,
+                                          None, None, dropout_p=p_hid, rng=rng,
                                           rng_stream=sp.rng_base + 3, **wait)
+            _ln_pgrad(dy2, sv["z2"], sv["mean2"], sv["rstd2"], sp.g2, sp.b2n)
             g2 = dz2d if dz2d is not None else dz2
             _wgrad(g2, sv["inter"], sp.w2, sp.b2)
             if sp.has_body:
@@ -316,8 +317,9 @@ class BertSpanFn(torch.autograd.Function):
             else:
                 dy1 = d_a
             dz1, dz1d = nat.layernorm_bwd(dy1, sv["z1"], sv["mean1"], sv["rstd1"], sp.g1.master(),
-                                          sp.g1.grad(), sp.b1n.grad(), dropout_p=p_hid, rng=rng,
+                                          None, None, dropout_p=p_hid, rng=rng,
                                           rng_stream=sp.rng_base + 2, **wait)
+            _ln_pgrad(dy1, sv["z1"], sv["mean1"], sv["rstd1"], sp.g1, sp.b1n)
             g1 = dz1d if dz1d is not None else dz1
             _wgrad(g1, sv["ctxt"], sp.wo, sp.bo)
             dctx = nat.gemm(g1, sp.wo.shadow(), b_mn=True)
@@ -367,10 +369,36 @@ def flush_wgrads() -> list:
     tensors so that a caller that flushed onto a side stream can keep them alive until it joins."""
     q = list(_WGRAD_QUEUE)
     _WGRAD_QUEUE.clear()
-    for g, act, wbank, bbank in q:
+    for item in q:
+        _run_param_grad(item)
+    return q
+
+
+def _run_param_grad(item) -> None:
+    if item[0] == "ln":
+        _, dy, z, mean, rstd, gbank, bbank = item
+        nat.ln_param_grad(dy, z, mean, rstd, gbank.grad(), bbank.grad())
+    else:
+        g, act, wbank, bbank = item
         nat.gemm(g, act, a_mn=True, b_mn=True, out=wbank.grad(), accumulate=True)
         nat.colsum_(g, bbank.grad())
-    return q
+
+
+def _ln_pgrad(dy, z, mean, rstd, gbank: ParamBank, bbank: ParamBank) -> None:
+    """LayerNorm gamma / beta gradients: like the weight gradients they are not needed by the
+    previous stage, so they follow the same deferral / side-stream policy."""
+    item = ("ln", dy, z, mean, rstd, gbank, bbank)
+    if _DEFER_WGRAD[0]:
+        _WGRAD_QUEUE.append(item)
+        return
+    side = _WGRAD_STREAM[0]
+    if side is not None:
+        side.wait_stream(torch.cuda.current_stream(dy.device))
+        with torch.cuda.stream(side):
+            _run_param_grad(item)
+        _WGRAD_KEEP.append((dy, z, mean, rstd))
+        return
+    _run_param_grad(item)
 
 
 def pending_wgrads() -> int:

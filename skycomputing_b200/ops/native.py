@@ -34,7 +34,7 @@ def available() -> bool:
 
 # ---- launch accounting (bench.py reports how many of OUR kernels ran in the timed region) ----
 _KERNELS_PER_CALL = {
-    "gemm": 1, "layernorm_fwd": 1, "layernorm_bwd": 2, "colsum": 1, "dgelu_mul": 1,
+    "gemm": 1, "layernorm_fwd": 1, "layernorm_bwd": 1, "ln_param_grad": 1, "colsum": 1, "dgelu_mul": 1,
     "attention_fwd": 1, "attention_bwd": 1, "embed_fwd": 1, "embed_bwd": 1,
     "small_linear_fwd": 1, "small_linear_bwd": 2, "softmax_ce": 1, "sgd_multi": 1,
     "cast_f32_to_bf16": 1, "cast_bf16_to_f32": 1, "advance_counter": 1, "advance_epoch": 1,
@@ -223,7 +223,8 @@ def layernorm_fwd(z, gamma, beta, eps: float = 1e-12, *, y=None, wait_flags: int
 def layernorm_bwd(dy, z, mean, rstd, gamma, dgamma, dbeta, *, dropout_p: float = 0.0,
                   rng: Optional[RngState] = None, rng_stream: int = 0, wait_flags: int = 0,
                   wait_epoch: int = 0, wait_mult: int = 0, error_flag: int = 0):
-    """Returns (dz, dz_dropped or None); dgamma/dbeta (fp32) are accumulated in place."""
+    """Returns (dz, dz_dropped or None); dgamma/dbeta (fp32) are accumulated in place, or left to a
+    later `ln_param_grad` call when passed as None."""
     _check(dy, torch.bfloat16, "dy")
     _check(z, torch.bfloat16, "z")
     M, H = z.shape
@@ -231,12 +232,19 @@ def layernorm_bwd(dy, z, mean, rstd, gamma, dgamma, dbeta, *, dropout_p: float =
     dzd = torch.empty_like(z) if dropout_p > 0 else None
     ext().layernorm_bwd(dy=dy.data_ptr(), z=z.data_ptr(), mean=mean.data_ptr(),
                         rstd=rstd.data_ptr(), gamma=gamma.data_ptr(), dz=dz.data_ptr(),
-                        dz_dropped=_ptr(dzd), dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(),
+                        dz_dropped=_ptr(dzd), dgamma=_ptr(dgamma), dbeta=_ptr(dbeta),
                         M=M, H=H, dropout_p=float(dropout_p),
                         rng_state=0 if rng is None else rng.ptr, rng_stream=rng_stream,
                         wait_flags=wait_flags, wait_epoch=wait_epoch, wait_mult=wait_mult,
                         error_flag=error_flag, stream=_stream())
     return dz, dzd
+
+
+def ln_param_grad(dy, z, mean, rstd, dgamma, dbeta) -> None:
+    """dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (the second half of layernorm_bwd)."""
+    M, H = z.shape
+    ext().ln_param_grad(dy=dy.data_ptr(), z=z.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr(),
+                        dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), M=M, H=H, stream=_stream())
 
 
 def colsum_(x: torch.Tensor, out: torch.Tensor) -> None:
