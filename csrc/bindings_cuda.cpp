@@ -261,7 +261,7 @@ void softmax_ce(uintptr_t logits, uintptr_t labels, uintptr_t loss, uintptr_t dl
 
 // descriptors: list of (p, g, mom, p_bf16, numel) -> packed host bytes to upload once
 py::bytes pack_sgd_descriptors(
-    const std::vector<std::tuple<uintptr_t, uintptr_t, uintptr_t, uintptr_t, long long>>& ts) {
+    const std::vector<std::tuple<uintptr_t, uintptr_t, uintptr_t, uintptr_t, long long, int>>& ts) {
   std::vector<sky::SgdTensor> v(ts.size());
   for (size_t i = 0; i < ts.size(); ++i) {
     v[i].p = P<float>(std::get<0>(ts[i]));
@@ -269,6 +269,8 @@ py::bytes pack_sgd_descriptors(
     v[i].mom = P<float>(std::get<2>(ts[i]));
     v[i].p_bf16 = P<void>(std::get<3>(ts[i]));
     v[i].numel = std::get<4>(ts[i]);
+    v[i].skip_zero = std::get<5>(ts[i]);
+    v[i].pad_ = 0;
   }
   return py::bytes(reinterpret_cast<const char*>(v.data()), v.size() * sizeof(sky::SgdTensor));
 }
@@ -379,13 +381,15 @@ PYBIND11_MODULE(_cuda, m) {
         py::arg("wait_flags") = 0, py::arg("wait_epoch") = 0, py::arg("wait_mult") = 0,
         py::arg("error_flag") = 0, py::arg("stream") = 0);
   m.def("ln_param_grad", [](uintptr_t dy, uintptr_t z, uintptr_t mean, uintptr_t rstd,
-                            uintptr_t dgamma, uintptr_t dbeta, int M, int H, uintptr_t stream) {
+                            uintptr_t dgamma, uintptr_t dbeta, int M, int H, uintptr_t x2,
+                            uintptr_t out2, uintptr_t stream) {
     check(sky::launch_ln_param_grad(P<void>(dy), P<void>(z), P<const float>(mean),
                                     P<const float>(rstd), P<float>(dgamma), P<float>(dbeta), M, H,
-                                    S(stream)),
+                                    P<void>(x2), P<float>(out2), S(stream)),
           "ln_param_grad");
   }, py::arg("dy"), py::arg("z"), py::arg("mean"), py::arg("rstd"), py::arg("dgamma"),
-        py::arg("dbeta"), py::arg("M"), py::arg("H"), py::arg("stream") = 0);
+        py::arg("dbeta"), py::arg("M"), py::arg("H"), py::arg("x2") = 0, py::arg("out2") = 0,
+        py::arg("stream") = 0);
   m.def("colsum", &colsum, py::arg("x"), py::arg("M"), py::arg("N"), py::arg("ldx"),
         py::arg("out"), py::arg("stream") = 0);
   m.def("attention_fwd", &attention_fwd, py::arg("qkv"), py::arg("mask"), py::arg("ctx"),

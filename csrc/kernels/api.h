@@ -105,7 +105,8 @@ struct LayerNormBwdArgs {
 };
 int launch_layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t stream);
 int launch_ln_param_grad(const void* dy, const void* z, const float* mean, const float* rstd,
-                         float* dgamma, float* dbeta, int M, int H, cudaStream_t stream);
+                         float* dgamma, float* dbeta, int M, int H, const void* x2, float* out2,
+                         cudaStream_t stream);
 
 // y[i] = g[i] * gelu'(h[i])  (bf16, n % 8 == 0): only used when a stage cut separates FFN1 | FFN2
 int launch_dgelu_mul(const void* g, const void* h, void* y, long long n, cudaStream_t stream);
@@ -212,6 +213,8 @@ struct SgdTensor {
   float* mom;         // may be null
   void* p_bf16;       // may be null
   long long numel;
+  int skip_zero;      // the first gradient write of the next step OVERWRITES g: do not zero it
+  int pad_;
 };
 int launch_sgd_multi(const SgdTensor* d_tensors, int n_tensors, long long max_numel, float lr,
                      float momentum, float weight_decay, float grad_scale, bool zero_grad,

@@ -247,11 +247,16 @@ layernorm_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
 __global__ void __launch_bounds__(256)
 ln_param_grad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ z,
                      const float* __restrict__ mean, const float* __restrict__ rstd,
-                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int H) {
+                     float* __restrict__ dgamma, float* __restrict__ dbeta, int M, int H,
+                     const __nv_bfloat16* __restrict__ x2, float* __restrict__ out2) {
+  // x2 / out2 (optional): out2[c] += sum_r x2[r,c] - the bias gradient of the dense layer in front
+  // of this LayerNorm (column sum of the LayerNorm input gradient), fused here to save a launch
   pdl_wait();
   pdl_launch_dependents();
   __shared__ float redg[8][256 + 8];
   __shared__ float redb[8][256 + 8];
+  __shared__ float red2[8][256 + 8];
+  float a2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const int cg = threadIdx.x & 31;
   const int rl = threadIdx.x >> 5;
   const int col = (blockIdx.x * 32 + cg) * 8;
@@ -272,25 +277,38 @@ ln_param_grad_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* 
         ab[2 * t] += fd.x;
         ab[2 * t + 1] += fd.y;
       }
+      if (x2 != nullptr) {
+        const uint4 ux = *reinterpret_cast<const uint4*>(x2 + static_cast<long long>(r) * H + col);
+        const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const float2 fx = unpack_bf16x2(wx[t]);
+          a2[2 * t] += fx.x;
+          a2[2 * t + 1] += fx.y;
+        }
+      }
     }
   }
 #pragma unroll
   for (int t = 0; t < 8; ++t) {
     redg[rl][cg * 8 + t] = ag[t];
     redb[rl][cg * 8 + t] = ab[t];
+    red2[rl][cg * 8 + t] = a2[t];
   }
   __syncthreads();
   const int c = threadIdx.x;
-  float sg = 0.f, sb = 0.f;
+  float sg = 0.f, sb = 0.f, s2 = 0.f;
 #pragma unroll
   for (int r = 0; r < 8; ++r) {
     sg += redg[r][c];
     sb += redb[r][c];
+    s2 += red2[r][c];
   }
   const int gc = blockIdx.x * 256 + c;
   if (gc < H) {
     if (dgamma) atomicAdd(&dgamma[gc], sg);
     if (dbeta) atomicAdd(&dbeta[gc], sb);
+    if (out2) atomicAdd(&out2[gc], s2);
   }
 }
 
@@ -730,7 +748,7 @@ sgd_multi_kernel(const SgdTensor* __restrict__ tensors, float lr, float momentum
     p.w -= lr * g.w;
     p4[i] = p;
     if (b4 != nullptr) b4[i] = make_uint2(pack_bf16x2(p.x, p.y), pack_bf16x2(p.z, p.w));
-    if (zero_grad) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (zero_grad && !t.skip_zero) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   // scalar tail
   if (blockIdx.x == 0) {
@@ -888,14 +906,16 @@ int launch_layernorm_bwd(const LayerNormBwdArgs& a, cudaStream_t stream) {
   if (e != cudaSuccess) return static_cast<int>(e);
   // NOTE: when gated on peer flags, the row kernel above has already waited for every panel.
   if (a.dgamma != nullptr || a.dbeta != nullptr)
-    return launch_ln_param_grad(a.dy, a.z, a.mean, a.rstd, a.dgamma, a.dbeta, a.M, a.H, stream);
+    return launch_ln_param_grad(a.dy, a.z, a.mean, a.rstd, a.dgamma, a.dbeta, a.M, a.H, nullptr,
+                                nullptr, stream);
   SKY_LAUNCH_CHECK();
 }
 
 // dgamma += sum_rows dy * xhat, dbeta += sum_rows dy.  A separate entry point so that the engine
 // can take it off the input-gradient critical path (it is queued with the weight gradients).
 int launch_ln_param_grad(const void* dy, const void* z, const float* mean, const float* rstd,
-                         float* dgamma, float* dbeta, int M, int H, cudaStream_t stream) {
+                         float* dgamma, float* dbeta, int M, int H, const void* x2, float* out2,
+                         cudaStream_t stream) {
   if (M <= 0) return 0;
   dim3 g2((H + 255) / 256, 1);
   int ry = (M + 63) / 64;
@@ -904,7 +924,7 @@ int launch_ln_param_grad(const void* dy, const void* z, const float* mean, const
   g2.y = ry;
   launch_pdl(ln_param_grad_kernel, g2, dim3(256), 0, stream,
              reinterpret_cast<const __nv_bfloat16*>(dy), reinterpret_cast<const __nv_bfloat16*>(z),
-             mean, rstd, dgamma, dbeta, M, H);
+             mean, rstd, dgamma, dbeta, M, H, reinterpret_cast<const __nv_bfloat16*>(x2), out2);
   SKY_LAUNCH_CHECK();
 }
 

@@ -52,6 +52,13 @@ class ParamBank:
         self._shadow: Optional[torch.Tensor] = None
         self._versions: List[int] = []
         self._ptrs: List[int] = []
+        # weight banks whose gradient is produced by the wgrad GEMM: the fused optimizer may leave
+        # the gradient un-zeroed (`overwrite_first`) and flag it `fresh`; the first wgrad of the
+        # next step then STORES instead of accumulating (saves 4 B/parameter of SGD traffic and
+        # turns that epilogue's red.add into plain stores)
+        self.wgrad_target = False
+        self.overwrite_first = False
+        self.fresh = False
 
     def _materialise(self) -> None:
         p0 = self.params[0]
@@ -118,7 +125,7 @@ class ParamBank:
         return (self.flat.data_ptr(), self.flat_grad.data_ptr(),
                 0 if momentum_buf is None else momentum_buf.data_ptr(),
                 self._shadow.data_ptr() if (self.need_shadow and self._shadow is not None) else 0,
-                self.flat.numel())
+                self.flat.numel(), 1 if self.overwrite_first else 0)
 
 
 class SpanParams:
@@ -278,9 +285,9 @@ class BertSpanFn(torch.autograd.Function):
             dz2, dz2d = nat.layernorm_bwd(dy2, sv["z2"], sv["mean2"], sv["rstd2"], sp.g2.master(),
                                           None, None, dropout_p=p_hid, rng=rng,
                                           rng_stream=sp.rng_base + 3, **wait)
-            _ln_pgrad(dy2, sv["z2"], sv["mean2"], sv["rstd2"], sp.g2, sp.b2n)
             g2 = dz2d if dz2d is not None else dz2
-            _wgrad(g2, sv["inter"], sp.w2, sp.b2)
+            _ln_pgrad(dy2, sv["z2"], sv["mean2"], sv["rstd2"], sp.g2, sp.b2n, g2, sp.b2)
+            _wgrad(g2, sv["inter"], sp.w2, None)
             if sp.has_body:
                 d_h1 = nat.gemm(g2, sp.w2.shadow(), b_mn=True, aux=sv["h1"], act=nat.ACT_DGELU_MUL_AUX)
             else:
@@ -319,9 +326,9 @@ class BertSpanFn(torch.autograd.Function):
             dz1, dz1d = nat.layernorm_bwd(dy1, sv["z1"], sv["mean1"], sv["rstd1"], sp.g1.master(),
                                           None, None, dropout_p=p_hid, rng=rng,
                                           rng_stream=sp.rng_base + 2, **wait)
-            _ln_pgrad(dy1, sv["z1"], sv["mean1"], sv["rstd1"], sp.g1, sp.b1n)
             g1 = dz1d if dz1d is not None else dz1
-            _wgrad(g1, sv["ctxt"], sp.wo, sp.bo)
+            _ln_pgrad(dy1, sv["z1"], sv["mean1"], sv["rstd1"], sp.g1, sp.b1n, g1, sp.bo)
+            _wgrad(g1, sv["ctxt"], sp.wo, None)
             dctx = nat.gemm(g1, sp.wo.shadow(), b_mn=True)
             dqkv = nat.attention_bwd(sv["qkv"], sv["mask2"], sv["ctxt"], sv["lse"], dctx, B, S,
                                      sp.heads, dropout_p=p_attn, rng=rng, rng_stream=sp.rng_base + 1)
@@ -376,18 +383,24 @@ def flush_wgrads() -> list:
 
 def _run_param_grad(item) -> None:
     if item[0] == "ln":
-        _, dy, z, mean, rstd, gbank, bbank = item
-        nat.ln_param_grad(dy, z, mean, rstd, gbank.grad(), bbank.grad())
+        _, dy, z, mean, rstd, gbank, bbank, x2, bias_bank = item
+        nat.ln_param_grad(dy, z, mean, rstd, gbank.grad(), bbank.grad(), x2,
+                          None if bias_bank is None else bias_bank.grad())
     else:
         g, act, wbank, bbank = item
-        nat.gemm(g, act, a_mn=True, b_mn=True, out=wbank.grad(), accumulate=True)
-        nat.colsum_(g, bbank.grad())
+        wbank.wgrad_target = True
+        first = wbank.overwrite_first and wbank.fresh
+        wbank.fresh = False
+        nat.gemm(g, act, a_mn=True, b_mn=True, out=wbank.grad(), accumulate=not first)
+        if bbank is not None:  # else: the column sum rides in the LayerNorm parameter-gradient kernel
+            nat.colsum_(g, bbank.grad())
 
 
-def _ln_pgrad(dy, z, mean, rstd, gbank: ParamBank, bbank: ParamBank) -> None:
+def _ln_pgrad(dy, z, mean, rstd, gbank: ParamBank, bbank: ParamBank, x2=None,
+              bias_bank: Optional[ParamBank] = None) -> None:
     """LayerNorm gamma / beta gradients: like the weight gradients they are not needed by the
     previous stage, so they follow the same deferral / side-stream policy."""
-    item = ("ln", dy, z, mean, rstd, gbank, bbank)
+    item = ("ln", dy, z, mean, rstd, gbank, bbank, x2, bias_bank)
     if _DEFER_WGRAD[0]:
         _WGRAD_QUEUE.append(item)
         return
@@ -396,7 +409,7 @@ def _ln_pgrad(dy, z, mean, rstd, gbank: ParamBank, bbank: ParamBank) -> None:
         side.wait_stream(torch.cuda.current_stream(dy.device))
         with torch.cuda.stream(side):
             _run_param_grad(item)
-        _WGRAD_KEEP.append((dy, z, mean, rstd))
+        _WGRAD_KEEP.append((dy, z, mean, rstd, x2))
         return
     _run_param_grad(item)
 
@@ -405,21 +418,22 @@ def pending_wgrads() -> int:
     return len(_WGRAD_QUEUE)
 
 
-def _wgrad(g: torch.Tensor, act: torch.Tensor, wbank: ParamBank, bbank: ParamBank) -> None:
-    """dW += g^T act (both operands MN-major over the token dimension), db += colsum(g)."""
+def _wgrad(g: torch.Tensor, act: torch.Tensor, wbank: ParamBank,
+           bbank: Optional[ParamBank]) -> None:
+    """dW += g^T act (both operands MN-major over the token dimension), db += colsum(g) unless
+    ``bbank`` is None (the column sum then rides in the LayerNorm parameter-gradient kernel)."""
+    item = (g, act, wbank, bbank)
     if _DEFER_WGRAD[0]:
-        _WGRAD_QUEUE.append((g, act, wbank, bbank))
+        _WGRAD_QUEUE.append(item)
         return
     side = _WGRAD_STREAM[0]
     if side is not None:
         side.wait_stream(torch.cuda.current_stream(g.device))
         with torch.cuda.stream(side):
-            nat.gemm(g, act, a_mn=True, b_mn=True, out=wbank.grad(), accumulate=True)
-            nat.colsum_(g, bbank.grad())
+            _run_param_grad(item)
         _WGRAD_KEEP.append((g, act))
         return
-    nat.gemm(g, act, a_mn=True, b_mn=True, out=wbank.grad(), accumulate=True)
-    nat.colsum_(g, bbank.grad())
+    _run_param_grad(item)
 
 
 def _dummy_out(like: torch.Tensor) -> torch.Tensor:

@@ -240,11 +240,18 @@ def layernorm_bwd(dy, z, mean, rstd, gamma, dgamma, dbeta, *, dropout_p: float =
     return dz, dzd
 
 
-def ln_param_grad(dy, z, mean, rstd, dgamma, dbeta) -> None:
-    """dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (the second half of layernorm_bwd)."""
+def ln_param_grad(dy, z, mean, rstd, dgamma, dbeta, x2=None, out2=None) -> None:
+    """dgamma += sum_rows dy * xhat, dbeta += sum_rows dy (the second half of layernorm_bwd);
+    optionally also out2 += column sums of x2 ([M,H] bf16): the bias gradient of the dense layer
+    in front of the LayerNorm, fused to save a launch."""
     M, H = z.shape
+    if x2 is not None:
+        _check(x2, torch.bfloat16, "x2")
+        if tuple(x2.shape) != (M, H) or not x2.is_contiguous():
+            raise ValueError("x2 must be a contiguous [M,H] tensor")
     ext().ln_param_grad(dy=dy.data_ptr(), z=z.data_ptr(), mean=mean.data_ptr(), rstd=rstd.data_ptr(),
-                        dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), M=M, H=H, stream=_stream())
+                        dgamma=dgamma.data_ptr(), dbeta=dbeta.data_ptr(), M=M, H=H, x2=_ptr(x2),
+                        out2=_ptr(out2), stream=_stream())
 
 
 def colsum_(x: torch.Tensor, out: torch.Tensor) -> None:

@@ -49,10 +49,17 @@ class FusedSGD:
                      [None] * len(self.banks))
         self._desc_dev: Optional[torch.Tensor] = None
         self._max_numel = 0
+        import os as _os
+
+        self._overwrite_ok = _os.environ.get("SKY_SGD_OVERWRITE", "1") != "0"
         self.param_groups = [dict(lr=lr, momentum=momentum, weight_decay=weight_decay)]
 
     def _descriptors(self) -> torch.Tensor:
         if self._desc_dev is None and self.banks:
+            # banks that received a wgrad GEMM in the first backward pass will receive one in every
+            # step: their gradient need not be zeroed, the next step's first wgrad overwrites it
+            for b in self.banks:
+                b.overwrite_first = bool(getattr(b, "wgrad_target", False)) and self._overwrite_ok
             descs = [b.sgd_descriptor(m) for b, m in zip(self.banks, self._mom)]
             raw = self._nat.ext().pack_sgd_descriptors(descs)
             host = torch.frombuffer(bytearray(raw), dtype=torch.uint8)
@@ -69,6 +76,9 @@ class FusedSGD:
                                       weight_decay=float(self.weight_decay),
                                       grad_scale=float(grad_scale), zero_grad=True,
                                       stream=torch.cuda.current_stream().cuda_stream)
+            for b in self.banks:
+                if b.overwrite_first:
+                    b.fresh = True
         if self._rest_opt is not None:
             self._rest_opt.step()
             self._rest_opt.zero_grad(set_to_none=False)
@@ -76,6 +86,7 @@ class FusedSGD:
     def zero_grad(self, set_to_none: bool = False) -> None:
         for b in self.banks:
             b.grad().zero_()
+            b.fresh = False
         if self._rest_opt is not None:
             self._rest_opt.zero_grad(set_to_none=False)
 

@@ -54,7 +54,8 @@ class Runner:
     def __init__(self, model, parameter_server, worker_manager, optimizer, max_epochs: int,
                  max_iters: int, loss_cfg: dict, timer_cfg: dict, logging_cfg: dict,
                  micro_batches: int = 1, schedule: Optional[str] = None, boundary: str = "auto",
-                 use_cuda_graph: bool = True, loss_interval: int = 1, device=None):
+                 use_cuda_graph: bool = True, loss_interval: int = 1, device=None,
+                 async_loss: bool = False):
         import torch.distributed as dist
 
         self.model = model
@@ -86,6 +87,12 @@ class Runner:
         self.micro_batches = micro_batches
         self.schedule = schedule or ("sequential" if micro_batches == 1 else "1f1b")
         self.loss_interval = loss_interval
+        # async_loss: the loss of step i is copied D2H asynchronously into pinned memory and
+        # handed out by the call for step i+1 (flush_loss() returns the last one), so the host
+        # never stalls the device between steps
+        self.async_loss = async_loss
+        self._loss_slots = None
+        self._loss_pending = None
         self.last_loss: Optional[float] = None
         self.last_step_seconds: Optional[float] = None
         from ..parallel.pipeline import PipelineEngine
@@ -158,9 +165,32 @@ class Runner:
         loss = eng.train_step(inputs, lab)
         out = None
         if loss is not None and self.loss_interval and (self._iter % self.loss_interval == 0):
-            out = float(loss.item())  # D2H read of the step's result
-            self.last_loss = out
+            if self.async_loss and loss.is_cuda:
+                out = self.flush_loss()  # the previous step's loss (its copy finished long ago)
+                if self._loss_slots is None:
+                    self._loss_slots = [torch.zeros(1, dtype=torch.float32).pin_memory()
+                                        for _ in range(2)]
+                    self._loss_slot_idx = 0
+                slot = self._loss_slots[self._loss_slot_idx]
+                self._loss_slot_idx ^= 1
+                slot.copy_(loss.detach().reshape(1), non_blocking=True)  # D2H of this step's result
+                ev = torch.cuda.Event()
+                ev.record()
+                self._loss_pending = (slot, ev)
+            else:
+                out = float(loss.item())  # D2H read of the step's result
+                self.last_loss = out
         return out
+
+    def flush_loss(self) -> Optional[float]:
+        """async_loss mode: wait for and return the most recent step's loss."""
+        if self._loss_pending is None:
+            return None
+        slot, ev = self._loss_pending
+        self._loss_pending = None
+        ev.synchronize()
+        self.last_loss = float(slot[0])
+        return self.last_loss
 
     def train(self, data_loader) -> None:
         self.data_loader = data_loader

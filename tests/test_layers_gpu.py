@@ -175,3 +175,43 @@ def test_training_step_decreases_loss_single_gpu():
         assert losses[-1] < losses[0] * 0.8, losses
     finally:
         set_backend("auto")
+
+
+def test_overwrite_first_gradients_match_zeroed_gradients():
+    """FusedSGD leaves the wgrad-GEMM targets un-zeroed and the next step's first weight gradient
+    overwrites them: after several steps the weights must equal those of the zero-every-step path."""
+    from skycomputing_b200.builder import ModuleWrapper
+    from skycomputing_b200.models import advance_rng, set_backend
+    from skycomputing_b200.parallel import build_optimizer
+    from skycomputing_b200.runner import build_loss
+
+    cfg = _cfg(p=0.0)
+    set_backend("native")
+    try:
+        finals = []
+        for overwrite in (True, False):
+            torch.manual_seed(0)
+            stack = _build(["BertEmbeddings", "BertLayer_Head", "BertLayer_Body", "BertLayer_Tail",
+                            "BertPooler", "BertTailForClassification"], cfg)
+            mw = ModuleWrapper(rank=0, module=stack, module_to_cuda=True, cuda_device=0)
+            mw.train()
+            opt = build_optimizer(mw, dict(optim_type="SGD", lr=0.05))
+            opt._overwrite_ok = overwrite
+            loss_fn = build_loss(dict(type="CrossEntropyLoss"), torch.device("cuda"))
+            g = torch.Generator(device="cuda").manual_seed(5)
+            B, S = 8, 128
+            ids = torch.randint(0, 1000, (B, S), device="cuda", generator=g)
+            tt = torch.zeros(B, S, dtype=torch.long, device="cuda")
+            m = torch.ones(B, S, dtype=torch.long, device="cuda")
+            labels = torch.randint(0, 3, (B,), device="cuda", generator=g)
+            for _ in range(5):
+                advance_rng()
+                loss_fn(mw(ids, tt, m)[0], labels).backward()
+                opt.step()
+            if overwrite:
+                assert any(b.overwrite_first for b in opt.banks)
+            finals.append(torch.cat([p.detach().float().flatten() for p in mw.parameters()]))
+        diff = (finals[0] - finals[1]).abs().max().item()
+        assert diff < 1e-4, diff
+    finally:
+        set_backend("auto")
