@@ -253,9 +253,9 @@ void small_linear_bwd(uintptr_t x, bool x_bf16, int ldx, uintptr_t w, uintptr_t 
         "small_linear_bwd");
 }
 void softmax_ce(uintptr_t logits, uintptr_t labels, uintptr_t loss, uintptr_t dlogits, int M,
-                int C, float grad_scale, uintptr_t stream) {
+                int C, float grad_scale, uintptr_t loss_acc, uintptr_t stream) {
   check(sky::launch_softmax_ce(P<const float>(logits), P<const int64_t>(labels), P<float>(loss),
-                               P<float>(dlogits), M, C, grad_scale, S(stream)),
+                               P<float>(dlogits), M, C, grad_scale, P<float>(loss_acc), S(stream)),
         "softmax_ce");
 }
 
@@ -423,7 +423,7 @@ PYBIND11_MODULE(_cuda, m) {
         py::arg("rng_stream") = 0, py::arg("stream") = 0);
   m.def("softmax_ce", &softmax_ce, py::arg("logits"), py::arg("labels"), py::arg("loss"),
         py::arg("dlogits"), py::arg("M"), py::arg("C"), py::arg("grad_scale") = 1.f,
-        py::arg("stream") = 0);
+        py::arg("loss_acc") = 0, py::arg("stream") = 0);
   m.def("pack_sgd_descriptors", &pack_sgd_descriptors);
   m.def("sgd_multi", &sgd_multi, py::arg("d_tensors"), py::arg("n"), py::arg("max_numel"),
         py::arg("lr"), py::arg("momentum") = 0.f, py::arg("weight_decay") = 0.f,

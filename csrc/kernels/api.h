@@ -200,7 +200,7 @@ int launch_small_linear_bwd(const void* x, bool x_bf16, int ldx, const float* w,
                             const uint64_t* rng_state, uint32_t rng_stream, cudaStream_t stream);
 // loss = mean_m CE(logits[m,:], labels[m]);  dlogits = (softmax - onehot) / M * grad_scale
 int launch_softmax_ce(const float* logits, const int64_t* labels, float* loss, float* dlogits,
-                      int M, int C, float grad_scale, cudaStream_t stream);
+                      int M, int C, float grad_scale, float* loss_acc, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
 // Optimizer / parameter maintenance

@@ -684,7 +684,7 @@ small_linear_dw_kernel(const void* __restrict__ x, bool x_bf16, long long ldx,
 __global__ void __launch_bounds__(256)
 softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ labels,
                   float* __restrict__ loss, float* __restrict__ dlogits, int M, int C,
-                  float grad_scale) {
+                  float grad_scale, float* __restrict__ loss_acc) {
   __shared__ float red[256];
   float local = 0.f;
   for (int m = threadIdx.x; m < M; m += blockDim.x) {
@@ -710,7 +710,12 @@ softmax_ce_kernel(const float* __restrict__ logits, const int64_t* __restrict__ 
     if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
     __syncthreads();
   }
-  if (threadIdx.x == 0) loss[0] = red[0] / static_cast<float>(M);
+  if (threadIdx.x == 0) {
+    const float mean = red[0] / static_cast<float>(M);
+    if (loss != nullptr) loss[0] = mean;
+    // micro-batched training: the step loss is the sum of the scaled micro-batch losses
+    if (loss_acc != nullptr) loss_acc[0] += mean * grad_scale;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1016,8 +1021,9 @@ int launch_small_linear_bwd(const void* x, bool x_bf16, int ldx, const float* w,
 }
 
 int launch_softmax_ce(const float* logits, const int64_t* labels, float* loss, float* dlogits,
-                      int M, int C, float grad_scale, cudaStream_t stream) {
-  softmax_ce_kernel<<<1, 256, 0, stream>>>(logits, labels, loss, dlogits, M, C, grad_scale);
+                      int M, int C, float grad_scale, float* loss_acc, cudaStream_t stream) {
+  softmax_ce_kernel<<<1, 256, 0, stream>>>(logits, labels, loss, dlogits, M, C, grad_scale,
+                                           loss_acc);
   SKY_LAUNCH_CHECK();
 }
 

@@ -297,11 +297,15 @@ def cast_f32_to_bf16_(src: torch.Tensor, dst: torch.Tensor) -> None:
     ext().cast_f32_to_bf16(src.data_ptr(), dst.data_ptr(), src.numel(), _stream())
 
 
-def softmax_ce(logits: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0):
+def softmax_ce(logits: torch.Tensor, labels: torch.Tensor, grad_scale: float = 1.0,
+               loss_acc: Optional[torch.Tensor] = None):
+    """Mean cross entropy and d(loss * grad_scale)/dlogits; ``loss_acc[0] += loss * grad_scale``
+    when given (the step loss of a micro-batched step, accumulated without extra launches)."""
     _check(logits, torch.float32, "logits")
     M, C = logits.shape
     loss = torch.empty(1, dtype=torch.float32, device=logits.device)
     dlogits = torch.empty_like(logits)
     ext().softmax_ce(logits=logits.data_ptr(), labels=labels.data_ptr(), loss=loss.data_ptr(),
-                     dlogits=dlogits.data_ptr(), M=M, C=C, grad_scale=grad_scale, stream=_stream())
+                     dlogits=dlogits.data_ptr(), M=M, C=C, grad_scale=grad_scale,
+                     loss_acc=_ptr(loss_acc), stream=_stream())
     return loss, dlogits

@@ -231,8 +231,13 @@ class PipelineEngine:
         loss = None
         if self.is_last:
             logits = outs[0]
-            loss = self.loss_fn(logits, labels_chunks[j]) / self.m
-            self._loss_acc += loss.detach().float()
+            if hasattr(self.loss_fn, "fused") and logits.is_cuda and self._loss_acc.dtype == torch.float32:
+                # (dlogits,) instead of a scalar loss: see _NativeCrossEntropy.fused
+                loss = (self.loss_fn.fused(logits, labels_chunks[j], 1.0 / self.m,
+                                           self._loss_acc.view(1)),)
+            else:
+                loss = self.loss_fn(logits, labels_chunks[j]) / self.m
+                self._loss_acc += loss.detach().float()
         return outs, loss
 
     def _backward(self, j: int, outs, loss, grads, args):
@@ -248,7 +253,10 @@ class PipelineEngine:
         self._mark(("B", j, "begin"))
         st.begin_backward()
         if self.is_last:
-            loss.backward()
+            if isinstance(loss, tuple):
+                torch.autograd.backward([outs[0]], [loss[0].to(outs[0].dtype)])
+            else:
+                loss.backward()
         elif self.out_fused:
             dummy = outs[0]
             torch.autograd.backward([dummy], [torch.zeros_like(dummy)])

@@ -37,6 +37,16 @@ class _NativeCrossEntropy(nn.Module):
 
         return SoftmaxCrossEntropyFn.apply(logits, labels)
 
+    def fused(self, logits, labels, scale: float, loss_acc: torch.Tensor) -> torch.Tensor:
+        """Engine fast path: one launch computes the micro-batch loss, adds ``loss * scale`` to
+        ``loss_acc`` and returns d(loss * scale)/dlogits, which the engine feeds straight into
+        ``logits.backward`` (no scalar-loss autograd nodes, no scaling / accumulation kernels)."""
+        from ..ops import native as nat
+
+        _, dlogits = nat.softmax_ce(logits.detach().contiguous().float(), labels.contiguous(),
+                                    grad_scale=scale, loss_acc=loss_acc)
+        return dlogits
+
 
 def build_loss(loss_cfg: dict, device: torch.device) -> nn.Module:
     cfg = dict(loss_cfg)
