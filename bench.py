@@ -126,7 +126,10 @@ def run_ours(args) -> dict:
 
     N = args.gpus
     global_batch = BATCH_PER_GPU * N
-    mb = args.micro_batch or (BATCH_PER_GPU if N == 1 else 16)
+    # micro-batch size: 32-sequence GEMMs run ~25 % more efficiently than 16-sequence ones, the
+    # 1F1B bubble shrinks with more micro-batches; measured cross-over between N=2 and N=4
+    # (profiles/bench_history.md)
+    mb = args.micro_batch or (BATCH_PER_GPU if N <= 2 else 16)
     micro_batches = max(1, global_batch // mb)
     cfg = BertConfig.bert_large()
     encoder = [dict(layer_type="BertLayer_Head", config=cfg.__dict__),
