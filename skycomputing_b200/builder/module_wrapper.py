@@ -53,6 +53,57 @@ class _BackwardProbe(torch.autograd.Function):
         return grad_output, None, None
 
 
+class BackwardSlowdownFunction(torch.autograd.Function):
+    """Stand-alone form of the backward probe with the reference's call signature
+    (scaelum/builder/module_wrapper.py:240-283): an identity on ``feat`` whose backward measures the
+    interval since the previous probe through ``timer`` (a ``DistributedTimer``), throttles for
+    ``interval * slowdown`` when ``do_slowdown`` and logs.  ``ModuleWrapper`` itself uses the
+    clone-free ``_BackwardProbe`` pair with device events; this class exists for code that builds
+    its own stages out of the reference's pieces.  Returns exactly one gradient per input (the
+    reference returns seven for six)."""
+
+    @staticmethod
+    def forward(ctx, feat, rank, slowdown, timer, logger, do_slowdown):
+        ctx.rank, ctx.slowdown, ctx.timer, ctx.logger = rank, slowdown, timer, logger
+        ctx.do_slowdown = do_slowdown
+        return feat.view_as(feat)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        timer, logger = ctx.timer, ctx.logger
+        if ctx.do_slowdown:
+            if grad_output.is_cuda:
+                torch.cuda.current_stream(grad_output.device).synchronize()
+            if timer is not None:
+                timer.add_timestamp()
+                try:
+                    interval = timer.get_prev_interval()
+                except (IndexError, ValueError):  # first stamp of the run: nothing to compare with
+                    interval = 0.0
+                if ctx.slowdown and interval > 0:
+                    time.sleep(interval * ctx.slowdown)
+                if logger is not None:
+                    logger.info("backward time on rank {}: {}".format(
+                        ctx.rank, interval * (1 + (ctx.slowdown or 0))))
+                timer.add_timestamp()
+        elif timer is not None:
+            timer.add_timestamp()
+        return grad_output, None, None, None, None, None
+
+
+class BackwardSlowdownModule(nn.Module):
+    """nn.Module face of :class:`BackwardSlowdownFunction` (scaelum module_wrapper.py:286-299)."""
+
+    def __init__(self, rank, slowdown, timer, logger, do_slowdown):
+        super().__init__()
+        self.rank, self.slowdown, self.timer, self.logger = rank, slowdown, timer, logger
+        self.do_slowdown = do_slowdown
+
+    def forward(self, data):
+        return BackwardSlowdownFunction.apply(data, self.rank, self.slowdown, self.timer,
+                                              self.logger, self.do_slowdown)
+
+
 class ModuleWrapper(nn.Module):
     def __init__(
         self,

@@ -102,6 +102,11 @@ def bias_gelu(bias, y):
     return gelu(bias + y)
 
 
+def bias_gelu_training(bias, y):
+    """Training-time variant of bias_gelu (scaelum bert_layers.py:36-38): bias add + library erf-GELU."""
+    return torch.nn.functional.gelu(bias + y)
+
+
 def bias_tanh(bias, y):
     return torch.tanh(bias + y)
 

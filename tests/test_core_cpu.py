@@ -256,3 +256,50 @@ def test_parameter_server_layer_indexed_roundtrip(tmp_path):
     lazy = sky.ParameterServer(cfg, lazy=True)
     lazy.load_weights_from_file(f)
     assert set(lazy.full_state_dict()) == set(ps.module_list.state_dict())
+
+
+def test_reference_named_helpers_exist_and_work(tmp_path):
+    """BackwardSlowdown{Function,Module}, call_method /
+    remote_method / parameter_rrefs, bias_gelu_training, glue.file_utils."""
+    import torch
+
+    import skycomputing_b200 as sky
+    from skycomputing_b200.builder import BackwardSlowdownFunction, BackwardSlowdownModule
+    from skycomputing_b200.dataset.glue import file_utils as fu
+    from skycomputing_b200.models.bert_layers import bias_gelu_training
+    from skycomputing_b200.utils import OwnerRef, call_method, parameter_rrefs, remote_method
+
+    # backward probe: identity, one gradient per input, throttles through the shared timer file
+    timer = sky.DistributedTimer(root=str(tmp_path))
+    x = torch.ones(4, requires_grad=True)
+    y = BackwardSlowdownModule(0, 0.0, timer, None, True)(x)
+    timer.add_timestamp()
+    (y * 2).sum().backward()
+    assert torch.equal(x.grad, torch.full((4,), 2.0))
+    assert BackwardSlowdownFunction.apply(x, 0, 0.0, None, None, False).shape == x.shape
+
+    lin = torch.nn.Linear(3, 2)
+    refs = parameter_rrefs(lin)
+    assert len(refs) == 2 and all(isinstance(r, OwnerRef) and r.is_owner() for r in refs)
+    assert remote_method(lambda p: tuple(p.shape), refs[0]) == (2, 3)
+    assert call_method(lambda p, k: p.numel() * k, refs[1], 3) == 6
+    assert refs[0].to_here() is refs[0].local_value()
+
+    out = bias_gelu_training(torch.zeros(3), torch.tensor([-1.0, 0.0, 1.0]))
+    assert torch.allclose(out, torch.nn.functional.gelu(torch.tensor([-1.0, 0.0, 1.0])))
+
+    # file cache: local path wins, cached URL copy wins, offline fetch fails with a usable message
+    p = tmp_path / "words.txt"
+    p.write_text("a\nb \n")
+    assert fu.cached_path(str(p)) == str(p)
+    assert fu.read_set_from_file(str(p)) == {"a", "b"}
+    url = "https://example.com/bert/vocab.txt"
+    cached = tmp_path / fu.url_to_filename(url)
+    cached.write_text("cached")
+    assert fu.cached_path(url, cache_dir=str(tmp_path)) == str(cached)
+    assert fu.get_file_extension("X/Y.TSV") == ".tsv" and fu.get_file_extension("a.b", dot=False) == "b"
+    assert fu.split_s3_path("s3://bucket/some/key") == ("bucket", "some/key")
+    assert fu.url_to_filename(url, "etag") != fu.url_to_filename(url)
+    import pytest
+    with pytest.raises(FileNotFoundError):
+        fu.cached_path(str(tmp_path / "missing.bin"))
