@@ -227,16 +227,18 @@ def test_device_benchmarker_single_process_with_slowdown_and_stimulate(monkeypat
     wm.load_worker_pool_from_config([
         dict(name="fast", server_config={}, extra_config=dict(slowdown=0, mem_limit=1000)),
         dict(name="slow", server_config={}, extra_config=dict(slowdown=3, mem_limit=500))])
-    gen = sky.build_data_generator("RandomTensorGenerator", generator_cfg=dict(size=(8, 64)))
-    db = sky.DeviceBenchmarker(wm, gen, model_config=[dict(layer_type="Linear", in_features=64,
-                                                           out_features=64)] * 4, iterations=5)
+    # big enough (and warmed up) that host timing noise cannot hide the 4x throttle
+    gen = sky.build_data_generator("RandomTensorGenerator", generator_cfg=dict(size=(256, 512)))
+    db = sky.DeviceBenchmarker(wm, gen, model_config=[dict(layer_type="Linear", in_features=512,
+                                                           out_features=512)] * 6, iterations=10,
+                               warmup=3)
     res = db.benchmark()
     assert list(res) == ["worker1", "worker2"]
     assert res["worker2"]["time"] > 2.0 * res["worker1"]["time"]
     assert res["worker1"]["avai_mem"] == 1000 and res["worker2"]["avai_mem"] == 500
     monkeypatch.setenv("STIMULATE", "1")
-    db2 = sky.DeviceBenchmarker(wm, gen, model_config=[dict(layer_type="Linear", in_features=64,
-                                                            out_features=64)], iterations=2)
+    db2 = sky.DeviceBenchmarker(wm, gen, model_config=[dict(layer_type="Linear", in_features=512,
+                                                            out_features=512)], iterations=2)
     res2 = db2.benchmark()
     s = sky.Stimulator(2)
     assert res2["worker1"]["avai_mem"] == pytest.approx(1000 / s.memory_slowdown(1))
