@@ -60,6 +60,7 @@ def main():
             t_local = timeit(lambda: _ln_fwd(z, g, b, 1e-12)) * 1e3
             t_peer = timeit(lambda: _ln_fwd(z, g, b, 1e-12, ch.peer_act_ptr(0),
                                             ch.peer_act_flags_ptr(0))) * 1e3
+            t_noflag = timeit(lambda: _ln_fwd(z, g, b, 1e-12, ch.peer_act_ptr(0), 0)) * 1e3
             name = "forward: LayerNorm -> next stage's HBM"
         else:
             ch = mgr.prev
@@ -70,6 +71,8 @@ def main():
             t_peer = timeit(lambda: nat.gemm(dqkv, w, b_mn=True, aux=aux, add_aux=True,
                                              out_ptr=ch.peer_grad_ptr(0), out_ld=ch.grad_ld,
                                              signal_flags=ch.peer_grad_flags_ptr(0))) * 1e3
+            t_noflag = timeit(lambda: nat.gemm(dqkv, w, b_mn=True, aux=aux, add_aux=True,
+                                               out_ptr=ch.peer_grad_ptr(0), out_ld=ch.grad_ld)) * 1e3
             name = "backward: QKV-dgrad GEMM epilogue -> previous stage's HBM"
         torch.cuda.synchronize()
         dist.barrier()
@@ -77,7 +80,7 @@ def main():
         t_nccl = nccl_p2p_us(buf, rank)
         roof = max(t_local, floor_us)
         row = dict(path=name, tokens=M, bytes=nbytes, nvlink_floor_us=round(floor_us, 2),
-                   kernel_local_us=round(t_local, 2), kernel_peer_us=round(t_peer, 2),
+                   kernel_local_us=round(t_local, 2), kernel_peer_us=round(t_peer, 2), kernel_peer_noflags_us=round(t_noflag, 2),
                    exposed_us=round(t_peer - t_local, 2), roofline_fraction=round(roof / t_peer, 3),
                    nccl_p2p_us=round(t_nccl, 2),
                    unfused_baseline_us=round(t_local + t_nccl, 2),
