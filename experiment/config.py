@@ -110,6 +110,10 @@ train_config = dict(
     optim_cfg=dict(optim_type="SGD", lr=0.001),
     loss_cfg=dict(type="CrossEntropyLoss"),
     runner_cfg=dict(max_epochs=1, max_iters=MAX_ITERS, micro_batches=MICRO_BATCHES),
-    hook_config=[dict(type="StopHook", root=_LOG_ROOT), dict(type="DistributedTimerHelperHook")],
+    hook_config=[dict(type="StopHook", root=_LOG_ROOT), dict(type="DistributedTimerHelperHook")]
+    # REALLOCATE_EVERY=N: re-benchmark the devices and re-run the allocator every N iterations,
+    # migrating layers when the predicted bottleneck improves (needs ALLOCATE_TYPE dynamic|optimal)
+    + ([dict(type="ReallocateHook", interval=int(os.getenv("REALLOCATE_EVERY")))]
+       if os.getenv("REALLOCATE_EVERY") else []),
     timer_config=dict(root=_LOG_ROOT),
 )

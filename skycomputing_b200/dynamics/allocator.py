@@ -65,6 +65,8 @@ class Allocator:
         self._device_flops_per_s = device_flops_per_s
         self._logger = logger
         self.last_result: Optional[dict] = None
+        self.last_device_times: dict = {}
+        self.last_layer_costs: list = []
 
     # ------------------------------------------------------------------ helpers
     def _log(self, msg: str) -> None:
@@ -79,6 +81,12 @@ class Allocator:
         dm = [float(results[n]["avai_mem"]) for n in names]
         lf, lm = self._model_benchmarker.benchmark()
         lf, lm = [float(x) for x in lf], [float(x) for x in lm]
+        # kept for diagnostics / ReallocateHook: benchmark time per PHYSICAL device (stable across
+        # re-orderings of the pool, unlike the rank-derived worker names) and the layer costs
+        pool = list(self._worker_manager.worker_pool)
+        self.last_device_times = {(w.device if w.device is not None else i): dt[i]
+                                  for i, w in enumerate(pool)}
+        self.last_layer_costs = list(lf)
         self._log("worker ranks: {}".format(ranks))
         self._log("worker time: {}".format(dt))
         return ranks, dt, dm, lf, lm

@@ -177,8 +177,26 @@ def run_process(rank: int, world_size: int, rpc_config: dict, model_config: list
                         logging_cfg=dict(logging_config), device=device,
                         **dict(train_config["runner_cfg"]))
         info("created runner")
+        def allocator_factory(pool):
+            """Same benchmarkers / options as the initial allocation, around a copy of the pool
+            (used by ReallocateHook to re-benchmark and re-allocate during training)."""
+            mb = model_benchmarker
+            db = None
+            if device_benchmarker is not None:
+                db = copy.copy(device_benchmarker)
+                db._worker_manager = pool
+            return Allocator(model_cfg=model_config, worker_manager=pool, model_benchmarker=mb,
+                             device_benchmarker=db, logger=logger, **alloc_opts)
+
         for cfg in train_config.get("hook_config", []):
             cfg = dict(cfg)
+            if cfg.get("type") == "ReallocateHook":
+                if model_benchmarker is None:
+                    info("ReallocateHook needs allocator_config.type dynamic|optimal: skipped")
+                    continue
+                cfg.setdefault("allocator_factory", allocator_factory)
+                cfg.setdefault("optimizer_cfg", dict(train_config["optim_cfg"]))
+                cfg.setdefault("allocate_type", alloc_type)
             runner.register_hook(build_hook(cfg.pop("type"), **cfg))
         info("register hooks")
         runner.train(data_loader)

@@ -105,14 +105,33 @@ class Runner:
         self._loss_pending = None
         self.last_loss: Optional[float] = None
         self.last_step_seconds: Optional[float] = None
+        self._boundary = boundary
+        self._use_cuda_graph = use_cuda_graph
+        self.engine = None
+        self._build_engine()
+
+    def _build_engine(self) -> None:
         from ..parallel.pipeline import PipelineEngine
 
+        model = self.model
         self.engine = PipelineEngine(
-            stage=stage, stage_index=model.local_stage_index, num_stages=model.num_stages,
-            stage_to_rank=model.stage_to_rank, device=self.device, optimizer=optimizer,
-            loss_fn=self.loss_function, micro_batches=micro_batches, schedule=self.schedule,
-            boundary=boundary, use_cuda_graph=use_cuda_graph)
+            stage=model.local_stage, stage_index=model.local_stage_index,
+            num_stages=model.num_stages, stage_to_rank=model.stage_to_rank, device=self.device,
+            optimizer=self.optimizer, loss_fn=self.loss_function, micro_batches=self.micro_batches,
+            schedule=self.schedule, boundary=self._boundary, use_cuda_graph=self._use_cuda_graph)
         model.attach_engine(self.engine)
+
+    def rebuild(self, model, optimizer, worker_manager=None) -> None:
+        """Swap in a re-partitioned model (ReallocateHook): the old engine's peer regions / CUDA
+        graph are released, a new engine is built around the new local stage.  Collective."""
+        if self.engine is not None:
+            self.engine.close()
+        self.model = model
+        self.optimizer = optimizer
+        if worker_manager is not None:
+            self.worker_manager = worker_manager
+        self._loss_pending = None
+        self._build_engine()
 
     # ------------------------------------------------------------------ properties
     hooks = property(lambda self: self._hooks)
@@ -230,10 +249,24 @@ class Runner:
                 self.last_step_seconds = step_s
                 self._log_iteration(step_s, loss, data)
                 self._iter += 1
+                self._check_boundary_health()
                 self._call_hook("after_train_iter")
             self._epoch += 1
             self._call_hook("after_train_epoch")
         self._call_hook("after_run")
+
+    def _check_boundary_health(self, every: int = 50) -> None:
+        """Failure detection for the in-kernel cross-GPU flag protocol: every spin-wait has a 4 s
+        timeout that raises a device-side error flag instead of hanging the GPU; poll it here
+        (one 4-byte D2H read every ``every`` iterations) and fail the run loudly."""
+        fused = getattr(self.engine, "fused", None)
+        if fused is None or self._iter % every != 0:
+            return
+        code = fused.error_code()
+        if code:
+            raise RuntimeError(
+                f"rank {self.rank}: fused stage-boundary wait timed out (error flag {code}) at "
+                f"iteration {self._iter}: a neighbour stage stopped producing - check its log")
 
     def _log_iteration(self, step_s: float, loss, data) -> None:
         stage = self.model.local_stage

@@ -196,3 +196,121 @@ def test_launcher_dynamic_allocation_two_workers(tmp_path):
     log = open(os.path.join(d, "allocation.log")).read()
     assert "dynamically allocated model layers" in log and log.count("number of layers") == 2
     assert os.path.exists(os.path.join(d, "metrics.jsonl"))
+
+
+def test_launcher_reallocation_hook_from_config(tmp_path):
+    """REALLOCATE_EVERY wires ReallocateHook through the launcher: the devices are re-benchmarked
+    during training and the decision (keep / migrate) is logged on rank 0."""
+    env = dict(os.environ, TINY="1", LAYER_NUM="4", CORE_NUM="3", DEVICE="cpu", MAX_ITERS="3",
+               PROJECT=str(tmp_path), ALLOCATE_TYPE="dynamic", MICRO_BATCHES="2", BATCH_SIZE="8",
+               REALLOCATE_EVERY="2")
+    from tests._dist_helpers import free_port
+
+    out = subprocess.run([sys.executable, "-m", "skycomputing_b200.launch", "-c",
+                          os.path.join(ROOT, "experiment", "config.py"), "--spawn", "2", "-p",
+                          str(free_port())], cwd=ROOT, env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    d = os.path.join(str(tmp_path), "logs", "3nodes_4layers", "dynamic")
+    log = open(os.path.join(d, "allocation.log")).read()
+    assert "reallocate:" in log, log
+
+
+# ---------------------------------------------------------------------------------------------
+# ReallocateHook: re-benchmark + re-allocate + migrate layers in the middle of a run
+# ---------------------------------------------------------------------------------------------
+class _FakeDeviceBench:
+    """Device 1 is 3x slower than device 0 (keyed like DeviceBenchmarker: worker name by rank)."""
+
+    def __init__(self, wm):
+        self._wm = wm
+
+    def benchmark(self):
+        from skycomputing_b200.utils import generate_worker_name
+
+        return {generate_worker_name(w.rank): dict(time=3.0 if w.device == 1 else 1.0, avai_mem=1e9)
+                for w in self._wm.worker_pool}
+
+
+class _FakeModelBench:
+    def __init__(self, n):
+        self._n = n
+
+    def benchmark(self):
+        return [1.0] * self._n, [1.0] * self._n
+
+
+def _train_with_reallocation(rank, world, use_hook, steps, tmp):
+    cfg = _model_cfg(layers=3)
+    wm = sky.WorkerManager(first_rank=0)
+    wm.load_worker_pool_from_config([
+        dict(name=f"w{i}", server_config={}, device=i,
+             extra_config=dict(slowdown=0, mem_limit=-1, timer_config=dict(root=tmp)))
+        for i in range(world)])
+    wm = sky.Allocator(cfg, wm, granularity="block").even_allocate()
+    model = sky.RpcModel(wm, this_rank=rank)
+    _seed_layers(model.local_stage, model.local_module.layer_range[0])
+    optim_cfg = dict(optim_type="SGD", lr=0.1)
+    opt = sky.build_optimizer(model.local_stage, dict(optim_cfg))
+    runner = sky.Runner(model=model, parameter_server=None, worker_manager=wm, optimizer=opt,
+                        max_epochs=1, max_iters=steps, loss_cfg=dict(type="CrossEntropyLoss"),
+                        timer_cfg=dict(root=tmp), logging_cfg=None, micro_batches=2,
+                        schedule="1f1b")
+    hook = None
+    if use_hook:
+        def factory(pool):
+            return sky.Allocator(cfg, pool, _FakeModelBench(len(cfg)), _FakeDeviceBench(pool),
+                                 granularity="block", solver="exact")
+
+        hook = sky.ReallocateHook(interval=2, allocator_factory=factory, optimizer_cfg=optim_cfg,
+                                  allocate_type="dynamic", min_gain=0.05)
+        runner.register_hook(hook)
+    dl = sky.build_dataloader_from_cfg(
+        dataset_cfg=dict(type="SynthMNLIDataset", num_samples=8 * steps, max_seq_length=16,
+                         vocab_size=100, seed=5),
+        dataloader_cfg=dict(batch_size=8, shuffle=False))
+    losses = []
+    orig = runner.train_iteration
+
+    def spy_iter(data, labels):
+        out = orig(data, labels)
+        if out is not None:
+            losses.append(out)
+        return out
+
+    runner.train_iteration = spy_iter
+    runner.train(dl)
+    sums = {}
+    mod = runner.model.local_module
+    b, _e = mod.layer_range
+    for off, sd in enumerate(mod.get_state_dict()):
+        sums[b + off] = float(sum(v.double().abs().sum() for v in sd.values()))
+    return dict(losses=losses, sums=sums, range=tuple(mod.layer_range),
+                migrations=0 if hook is None else hook.migrations,
+                decision=None if hook is None else hook.last_decision)
+
+
+def test_reallocate_hook_migrates_layers_without_changing_the_training_result(tmp_path):
+    tmp = str(tmp_path)
+    plain = run_distributed(_train_with_reallocation, 2, False, 5, tmp)
+    moved = run_distributed(_train_with_reallocation, 2, True, 5, tmp)
+    # even split of emb + 3 blocks + pooler + classifier at block granularity, then the 3x slower
+    # device 1 sheds blocks to device 0
+    assert plain[0]["range"] != moved[0]["range"]
+    assert moved[0]["migrations"] == 1 and moved[1]["migrations"] == 1   # iter 2 moves, iter 4 keeps
+    n0 = moved[0]["range"][1] - moved[0]["range"][0]
+    n1 = moved[1]["range"][1] - moved[1]["range"][0]
+    assert n0 > n1
+    assert moved[0]["decision"]["gain"] >= 0.0
+    # training is partition independent: same losses, same final weights layer by layer
+    lp = [r["losses"] for r in plain if r["losses"]][0]
+    lm = [r["losses"] for r in moved if r["losses"]][0]
+    assert lm == pytest.approx(lp, rel=1e-5)
+    sp, sm = {}, {}
+    for r in plain:
+        sp.update(r["sums"])
+    for r in moved:
+        sm.update(r["sums"])
+    assert sorted(sp) == sorted(sm) == list(range(12))
+    for k in sp:
+        assert sm[k] == pytest.approx(sp[k], rel=1e-6), k
