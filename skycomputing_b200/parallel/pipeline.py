@@ -538,3 +538,14 @@ class PipelineEngine:
         if self.fused is not None:
             self.fused.close()
             self.fused = None
+        # the gradient deferral / side stream are process-wide switches of ops.functions: hand them
+        # back so that code running without an engine afterwards gets inline gradients again
+        if self._defer_wgrad or self._wgrad_immediate:
+            from ..ops.functions import set_wgrad_deferral, set_wgrad_stream
+
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            if self._defer_wgrad:
+                set_wgrad_deferral(False)
+            set_wgrad_stream(None)
+            self._defer_wgrad = self._wgrad_immediate = False
