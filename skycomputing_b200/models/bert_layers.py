@@ -126,7 +126,24 @@ class LinearActivation(nn.Module):
         super().__init__()
         self.in_features, self.out_features = in_features, out_features
         self.act_name = act if isinstance(act, str) else None
-        self.act_fn = ACT2FN[act] if isinstance(act, str) else act
+        # reference semantics (bert_layers.py:73-84): with a bias, "gelu" means "bias_gelu" - the
+        # bias is handed to the activation instead of to F.linear; "bias_*" names are accepted
+        # directly.  `act_fn` is the plain activation, `biased_act_fn(bias, y)` the folded form.
+        self.biased_act_fn = None
+        if isinstance(act, str):
+            base = act[5:] if act.startswith("bias_") else act
+            folded = "bias_" + base
+            if folded in ACT2FN:
+                self.biased_act_fn = ACT2FN[folded]
+            if base in ACT2FN:
+                self.act_fn = ACT2FN[base]
+            elif self.biased_act_fn is not None:
+                fn = self.biased_act_fn
+                self.act_fn = lambda y: fn(torch.zeros((), dtype=y.dtype, device=y.device), y)
+            else:
+                raise KeyError(f"unknown activation {act!r}; known: {sorted(ACT2FN)}")
+        else:
+            self.act_fn = act
         self.weight = nn.Parameter(torch.empty(out_features, in_features))
         if bias:
             self.bias = nn.Parameter(torch.empty(out_features))
@@ -142,9 +159,11 @@ class LinearActivation(nn.Module):
 
     def forward(self, x):
         y = F.linear(x, self.weight, None)
-        if self.bias is not None:
-            y = y + self.bias
-        return self.act_fn(y)
+        if self.bias is None:
+            return self.act_fn(y)
+        if self.biased_act_fn is not None:
+            return self.biased_act_fn(self.bias, y)
+        return self.act_fn(y + self.bias)
 
     def extra_repr(self) -> str:
         return f"in_features={self.in_features}, out_features={self.out_features}, bias={self.bias is not None}"
