@@ -133,11 +133,6 @@ class PipelineEngine:
             in_ok, out_ok = self.stage.fused_boundary_support()
             spans = self.stage.spans()
             if spans:
-                sp = spans[0]
-                lay = sp.head or sp.body or sp.tail
-                for p in lay.parameters():
-                    hidden = p.shape[-1] if sp.tail is None else p.shape[0]
-                    break
                 hidden = self._hidden_size(spans[0])
             shape_ok = self.seq == 128 and hidden % 64 == 0 and (self.mb_batch * self.seq) % 128 == 0
             if spans and spans[0].head is not None:
@@ -535,6 +530,8 @@ class PipelineEngine:
         return outs
 
     def close(self) -> None:
+        if self.device.type == "cuda":
+            torch.cuda.synchronize(self.device)  # nothing of ours may still touch a peer region
         if self.fused is not None:
             self.fused.close()
             self.fused = None
@@ -543,8 +540,6 @@ class PipelineEngine:
         if self._defer_wgrad or self._wgrad_immediate:
             from ..ops.functions import set_wgrad_deferral, set_wgrad_stream
 
-            if self.device.type == "cuda":
-                torch.cuda.synchronize(self.device)
             if self._defer_wgrad:
                 set_wgrad_deferral(False)
             set_wgrad_stream(None)

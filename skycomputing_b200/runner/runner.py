@@ -125,6 +125,12 @@ class Runner:
         """Swap in a re-partitioned model (ReallocateHook): the old engine's peer regions / CUDA
         graph are released, a new engine is built around the new local stage.  Collective."""
         if self.engine is not None:
+            import torch.distributed as dist
+
+            if self.device.type == "cuda":
+                torch.cuda.synchronize(self.device)
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                dist.barrier()  # every rank is done with its neighbours' regions before any is freed
             self.engine.close()
         self.model = model
         self.optimizer = optimizer
