@@ -19,8 +19,7 @@ fused NVLink boundary exists for those cuts and they carry 5x less data than a c
 """
 from __future__ import annotations
 
-import math
-from typing import Dict, List, Optional, Sequence
+from typing import List, Optional, Sequence
 
 from .. import _core
 from .worker_manager import WorkerManager

@@ -32,8 +32,6 @@ class ParameterServer(nn.Module):
         return build_layer(cfg.pop("layer_type"), **cfg)
 
     def _build_model(self) -> None:
-        from ..models.bert_layers import get_backend, set_backend
-
         for idx in range(len(self._model_config)):
             self.module_list.append(self._build_layer(idx))
 

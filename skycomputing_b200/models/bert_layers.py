@@ -24,7 +24,7 @@ input lives on a CUDA device and the extension is built.
 from __future__ import annotations
 
 import math
-from typing import List, Optional
+from typing import List
 
 import torch
 import torch.nn as nn

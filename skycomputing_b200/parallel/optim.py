@@ -14,7 +14,7 @@ with the reference's DistributedOptimizer.
 """
 from __future__ import annotations
 
-from typing import List, Optional
+from typing import Optional
 
 import torch
 import torch.nn as nn

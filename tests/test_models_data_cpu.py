@@ -5,7 +5,6 @@ import json
 import math
 import os
 
-import pytest
 import torch
 
 import skycomputing_b200 as sky
