@@ -87,6 +87,9 @@ allocator_config = dict(
     type=ALLOCATE_TYPE,
     granularity=os.getenv("GRANULARITY", "block"),
     solver=os.getenv("SOLVER", "heuristic"),
+    # VIRTUAL_STAGES=v > 1: looped pipeline, every worker runs v non-adjacent chunks of the model
+    # (pipeline fill / drain shrink by v; parallel/pipeline_looped.py)
+    virtual_stages=int(os.getenv("VIRTUAL_STAGES", "1")),
     benchmark_config=dict(
         model=dict(device="cpu", param_scale=2,
                    data_generator_cfg=dict(generator_type="DataloaderGenerator",

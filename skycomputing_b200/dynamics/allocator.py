@@ -161,8 +161,55 @@ class Allocator:
         self._log("optimal allocation: {}".format(res))
         return self._assign(res["order"], res["boundaries"], units)
 
-    def allocate(self, alloc_type: str, **kwargs) -> WorkerManager:
+    def looped_allocate(self, alloc_type: str, virtual_stages: int) -> WorkerManager:
+        """Allocation for a LOOPED pipeline: ``virtual_stages`` (v) chunks per worker, virtual
+        stage k = chunk k // D of worker k % D (pool order is kept, no device permutation).
+
+        The v x D spans come from the same solvers: ``even`` splits the units evenly; ``dynamic``
+        / ``optimal`` run the exact fixed-order min-max partition over v x D virtual devices whose
+        speed is the worker's and whose memory cap is 1/v of the worker's.  With v chunks the
+        pipeline fill / drain shrink by v (parallel/pipeline_looped.py)."""
+        v = int(virtual_stages)
+        assert v >= 1
+        units = group_units(self._model_cfg, self._granularity)
+        pool = list(self._worker_manager.worker_pool)
+        D = len(pool)
+        VP = v * D
+        if len(units) < VP:
+            raise ValueError(f"{len(units)} allocatable units cannot fill {v} x {D} virtual stages")
+        if alloc_type in ("dynamic", "optimal"):
+            ranks, dt, dm, lf, lm = self._benchmarks()
+            _units, uf, um = self._unit_vectors(lf, lm)
+            vdt = [dt[k % D] for k in range(VP)]
+            vdm = [dm[k % D] / v for k in range(VP)]
+            res = _core.optimal_partition(uf, um, vdt, vdm, permute=False, min_layers=1,
+                                          cut_penalty=self._cut_penalty(units, vdt, uf))
+            bounds = res["boundaries"]
+            self.last_result = dict(res, virtual_stages=v)
+        else:
+            bounds = _core.even_partition(len(units), VP)
+            self.last_result = dict(method="even", boundaries=bounds, order=list(range(VP)),
+                                    virtual_stages=v)
+        for d, w in enumerate(pool):
+            chunks, cfg = [], []
+            for c in range(v):
+                k = c * D + d
+                b = units[bounds[k]][0]
+                e = units[bounds[k + 1] - 1][1]
+                chunks.append((b, e))
+                cfg += self._model_cfg[b:e]
+            w.chunks = chunks
+            w.model_config = cfg
+            w.layer_range = chunks[0] if v == 1 else None
+            w.order = d + 1
+            self._log("rank {} (device {}) runs layer spans {}".format(w.rank, w.device, chunks))
+        self._worker_manager.reset_rank_by_order()
+        return self._worker_manager
+
+    def allocate(self, alloc_type: str, virtual_stages: int = 1, **kwargs) -> WorkerManager:
         """Dispatch on ``allocator_config['type']`` (experiment/launch.py:119-138 semantics)."""
+        if virtual_stages and int(virtual_stages) > 1:
+            return self.looped_allocate(alloc_type, int(virtual_stages))
         if alloc_type == "dynamic":
             return self.dynamic_allocate(**kwargs)
         if alloc_type == "optimal":

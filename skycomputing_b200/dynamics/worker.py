@@ -16,7 +16,7 @@ class Worker:
                  worker_id: Optional[str] = None, order: Optional[int] = None,
                  model_config: Optional[list] = None, extra_config: Optional[dict] = None,
                  is_running: bool = False, device: Optional[int] = None,
-                 layer_range: Optional[tuple] = None) -> None:
+                 layer_range: Optional[tuple] = None, chunks: Optional[list] = None) -> None:
         self._rank = rank
         self._name = name
         self._is_running = is_running
@@ -27,6 +27,9 @@ class Worker:
         self._extra_config = extra_config or {}
         self._device = device
         self._layer_range = layer_range
+        # looped (virtual-stage) pipelines: this worker runs several NON-adjacent layer spans
+        # [(begin, end), ...]; virtual stage k of the pipeline is chunk k // D of worker k % D
+        self._chunks = chunks
 
     rank = property(lambda self: self._rank)
     id = property(lambda self: self._worker_id)
@@ -38,6 +41,7 @@ class Worker:
     order = property(lambda self: self._order)
     device = property(lambda self: self._device)
     layer_range = property(lambda self: self._layer_range)
+    chunks = property(lambda self: self._chunks)
 
     @property
     def env_config(self) -> dict:
@@ -66,6 +70,10 @@ class Worker:
     @layer_range.setter
     def layer_range(self, rng: Optional[tuple]) -> None:
         self._layer_range = rng
+
+    @chunks.setter
+    def chunks(self, chunks: Optional[list]) -> None:
+        self._chunks = chunks
 
     def serialize(self) -> dict:
         return dict(self.__dict__)

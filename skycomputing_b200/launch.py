@@ -156,7 +156,8 @@ def run_process(rank: int, world_size: int, rpc_config: dict, model_config: list
                               model_benchmarker=model_benchmarker,
                               device_benchmarker=device_benchmarker, logger=logger, **alloc_opts)
         try:
-            worker_manager = allocator.allocate(alloc_type)
+            worker_manager = allocator.allocate(
+                alloc_type, virtual_stages=int(allocator_config.get("virtual_stages", 1)))
         except Exception:
             info("allocation FAILED:\n" + traceback.format_exc())
             raise
@@ -168,7 +169,7 @@ def run_process(rank: int, world_size: int, rpc_config: dict, model_config: list
 
         model = RpcModel(worker_manager=worker_manager, this_rank=rank)
         info("created model")
-        optimizer = build_optimizer(model.local_stage, dict(train_config["optim_cfg"]))
+        optimizer = build_optimizer(model.optim_module, dict(train_config["optim_cfg"]))
         info("created distrubted optimizer")
         runner = Runner(model=model, parameter_server=parameter_server,
                         worker_manager=worker_manager, optimizer=optimizer,

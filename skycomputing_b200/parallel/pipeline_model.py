@@ -108,23 +108,40 @@ class RpcModel(nn.Module):
         assert isinstance(self.model, nn.ModuleList), "model must be iterable"
 
     def _build_model(self) -> nn.ModuleList:
+        """One module per (virtual) pipeline stage, in pipeline order.  Plain pipelines: stage k =
+        worker k.  Looped pipelines (``worker.chunks`` with v > 1 spans): virtual stage k = chunk
+        k // D of worker k % D, so a rank owns v LocalModules."""
         model = nn.ModuleList()
-        pool = self.worker_manager.worker_pool
-        single = len(pool) == 1
-        for stage_idx, worker in enumerate(pool):
-            dev = worker.device if worker.device is not None else stage_idx
+        pool = list(self.worker_manager.worker_pool)
+        D = len(pool)
+        single = D == 1
+        v = max((len(w.chunks) for w in pool if getattr(w, "chunks", None)), default=1)
+        self.virtual_stages = v if not single else 1
+        if self.virtual_stages > 1:
+            assert all(w.chunks is not None and len(w.chunks) == v for w in pool), \
+                "every worker of a looped pipeline needs the same number of chunks"
+        for k in range(D * self.virtual_stages):
+            d, c = k % D, k // D
+            worker = pool[d]
+            dev = worker.device if worker.device is not None else d
             cfg = dict(worker.extra_config or {})
+            if self.virtual_stages > 1:
+                b, e = worker.chunks[c]
+                off = sum(ce - cb for cb, ce in worker.chunks[:c])
+                model_cfg, layer_range = worker.model_config[off:off + (e - b)], (b, e)
+            else:
+                model_cfg, layer_range = worker.model_config, worker.layer_range
             if single or dev == self.this_rank:
                 if cfg.get("module_to_cuda") and torch.cuda.is_available():
                     # one process per GPU: the process' current device is the stage's device
                     cfg["cuda_device"] = torch.cuda.current_device()
-                module = LocalModule(rank=worker.rank, model_cfg=worker.model_config,
+                module = LocalModule(rank=worker.rank, model_cfg=model_cfg,
                                      sequential_wrapper_cfg=cfg, device_rank=dev,
-                                     layer_range=worker.layer_range)
+                                     layer_range=layer_range)
             else:
-                module = RemoteModule(rank=worker.rank, model_cfg=worker.model_config,
+                module = RemoteModule(rank=worker.rank, model_cfg=model_cfg,
                                       sequential_wrapper_cfg=cfg, device_rank=dev,
-                                      layer_range=worker.layer_range)
+                                      layer_range=layer_range)
             model.append(module)
         return model
 
@@ -143,6 +160,22 @@ class RpcModel(nn.Module):
             if m.is_local:
                 return i
         raise RuntimeError("this rank owns no pipeline stage")
+
+    @property
+    def local_stage_indices(self) -> List[int]:
+        """All (virtual) stages this rank owns, in pipeline order (one for a plain pipeline)."""
+        return [i for i, m in enumerate(self.model) if m.is_local]
+
+    @property
+    def local_stages(self) -> List:
+        return [self.model[i].module for i in self.local_stage_indices]
+
+    @property
+    def optim_module(self) -> nn.Module:
+        """What the optimizer of this rank must cover: the local stage, or all local chunks of a
+        looped pipeline."""
+        stages = self.local_stages
+        return stages[0] if len(stages) == 1 else nn.ModuleList(stages)
 
     @property
     def local_module(self) -> LocalModule:

@@ -113,7 +113,7 @@ class ReallocateHook(Hook):
                 b, e = module.layer_range
                 module.load_weights([per_layer[i] for i in range(b, e)])
         model.train(True)
-        optimizer = build_optimizer(model.local_stage, dict(self._optimizer_cfg))
+        optimizer = build_optimizer(model.optim_module, dict(self._optimizer_cfg))
         runner.rebuild(model, optimizer, worker_manager=new_wm)
         self.migrations += 1
         if self._on_migrate is not None:

@@ -114,6 +114,18 @@ class Runner:
         from ..parallel.pipeline import PipelineEngine
 
         model = self.model
+        v = getattr(model, "virtual_stages", 1)
+        if v > 1:
+            from ..parallel.pipeline_looped import LoopedPipelineEngine
+
+            P = model.num_stages // v
+            self.schedule = "looped"
+            self.engine = LoopedPipelineEngine(
+                stages=model.local_stages, virtual_indices=model.local_stage_indices, num_ranks=P,
+                ring=model.stage_to_rank[:P], device=self.device, optimizer=self.optimizer,
+                loss_fn=self.loss_function, micro_batches=self.micro_batches)
+            model.attach_engine(self.engine)
+            return
         self.engine = PipelineEngine(
             stage=model.local_stage, stage_index=model.local_stage_index,
             num_stages=model.num_stages, stage_to_rank=model.stage_to_rank, device=self.device,

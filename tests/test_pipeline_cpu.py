@@ -314,3 +314,104 @@ def test_reallocate_hook_migrates_layers_without_changing_the_training_result(tm
     assert sorted(sp) == sorted(sm) == list(range(12))
     for k in sp:
         assert sm[k] == pytest.approx(sp[k], rel=1e-6), k
+
+
+# ---------------------------------------------------------------------------------------------
+# Looped (virtual-stage) pipeline: v chunks per rank, ring of ranks
+# ---------------------------------------------------------------------------------------------
+def _train_looped(rank, world, virtual_stages, micro_batches, steps, tmp, alloc):
+    cfg = _model_cfg(layers=4)
+    wm = sky.WorkerManager(first_rank=0)
+    wm.load_worker_pool_from_config([
+        dict(name=f"w{i}", server_config={}, device=i,
+             extra_config=dict(slowdown=0, mem_limit=-1, timer_config=dict(root=tmp)))
+        for i in range(world)])
+    if alloc == "even":
+        allocator = sky.Allocator(cfg, wm, granularity="block")
+    else:
+        allocator = sky.Allocator(cfg, wm, _FakeModelBench(len(cfg)), _FakeDeviceBench(wm),
+                                  granularity="block", solver="exact")
+    wm = allocator.allocate(alloc, virtual_stages=virtual_stages)
+    model = sky.RpcModel(wm, this_rank=rank)
+    for mod in model.model:
+        if mod.is_local:
+            _seed_layers(mod.module, mod.layer_range[0])
+    opt = sky.build_optimizer(model.optim_module, dict(optim_type="SGD", lr=0.1))
+    runner = sky.Runner(model=model, parameter_server=None, worker_manager=wm, optimizer=opt,
+                        max_epochs=1, max_iters=steps, loss_cfg=dict(type="CrossEntropyLoss"),
+                        timer_cfg=dict(root=tmp), logging_cfg=None, micro_batches=micro_batches,
+                        schedule="1f1b" if micro_batches > 1 else "sequential")
+    dl = sky.build_dataloader_from_cfg(
+        dataset_cfg=dict(type="SynthMNLIDataset", num_samples=8 * steps, max_seq_length=16,
+                         vocab_size=100, seed=5),
+        dataloader_cfg=dict(batch_size=8, shuffle=False))
+    losses = []
+    orig = runner.train_iteration
+
+    def spy_iter(data, labels):
+        out = orig(data, labels)
+        if out is not None:
+            losses.append(out)
+        return out
+
+    runner.train_iteration = spy_iter
+    runner.train(dl)
+    sums = {}
+    for mod in runner.model.model:
+        if mod.is_local:
+            b, _e = mod.layer_range
+            for off, sd in enumerate(mod.get_state_dict()):
+                sums[b + off] = float(sum(v.double().abs().sum() for v in sd.values()))
+    return dict(losses=losses, sums=sums, schedule=runner.engine.schedule,
+                chunks=[list(w.chunks) if w.chunks else None for w in wm.worker_pool])
+
+
+def test_looped_pipeline_equals_plain_pipeline(tmp_path):
+    """v chunks per rank on a ring of ranks: same losses and the same final weights as the plain
+    one-span-per-rank pipeline (which equals single-stage training, tested above)."""
+    tmp = str(tmp_path)
+    plain = run_distributed(_train_looped, 2, 1, 2, 4, tmp, "even")
+    loop2 = run_distributed(_train_looped, 2, 2, 2, 4, tmp, "even")
+    loop3 = run_distributed(_train_looped, 3, 2, 4, 4, tmp, "even")
+    assert plain[0]["schedule"] != "looped" and loop2[0]["schedule"] == "looped"
+    assert loop2[0]["chunks"] == [[(0, 4), (10, 14)], [(4, 10), (14, 15)]]
+    lp = [r["losses"] for r in plain if r["losses"]][0]
+    l2 = [r["losses"] for r in loop2 if r["losses"]][0]
+    l3 = [r["losses"] for r in loop3 if r["losses"]][0]
+    assert len(lp) == 4 and l2 == pytest.approx(lp, rel=1e-5)
+    # 4 micro-batches of 2 vs 2 micro-batches of 4: the same mean loss per step
+    assert l3 == pytest.approx(lp, rel=1e-4)
+    sp, s2 = {}, {}
+    for r in plain:
+        sp.update(r["sums"])
+    for r in loop2:
+        s2.update(r["sums"])
+    assert sorted(sp) == sorted(s2) == list(range(15))
+    for k in sp:
+        assert s2[k] == pytest.approx(sp[k], rel=1e-6), k
+
+
+def test_looped_allocation_respects_device_speeds(tmp_path):
+    """Exact solver over v x D virtual devices: the 3x slower device gets the lighter chunks."""
+    out = run_distributed(_train_looped, 2, 2, 2, 2, str(tmp_path), "optimal")
+    chunks = out[0]["chunks"]
+    n0 = sum(e - b for b, e in chunks[0])
+    n1 = sum(e - b for b, e in chunks[1])
+    assert n0 > n1 and n0 + n1 == 15
+    assert [r["losses"] for r in out if r["losses"]][0][-1] > 0
+
+
+def test_launcher_looped_pipeline_from_config(tmp_path):
+    env = dict(os.environ, TINY="1", LAYER_NUM="4", CORE_NUM="3", DEVICE="cpu", MAX_ITERS="2",
+               PROJECT=str(tmp_path), ALLOCATE_TYPE="even", MICRO_BATCHES="2", BATCH_SIZE="8",
+               VIRTUAL_STAGES="2")
+    from tests._dist_helpers import free_port
+
+    out = subprocess.run([sys.executable, "-m", "skycomputing_b200.launch", "-c",
+                          os.path.join(ROOT, "experiment", "config.py"), "--spawn", "2", "-p",
+                          str(free_port())], cwd=ROOT, env=env, capture_output=True, text=True,
+                         timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    d = os.path.join(str(tmp_path), "logs", "3nodes_4layers", "even")
+    log = open(os.path.join(d, "allocation.log")).read()
+    assert "runs layer spans [(0, 4), (10, 14)]" in log and log.count("step time") == 2
