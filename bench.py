@@ -49,6 +49,9 @@ def parse_args():
     ap.add_argument("--boundary", type=str, default=os.environ.get("SKY_BOUNDARY", "auto"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--layers", type=int, default=LAYER_NUM)
+    # > 1: looped pipeline, v non-adjacent chunks per GPU (parallel/pipeline_looped.py); torch.
+    # distributed boundaries unless SKY_LOOPED_FUSED=1 (fused ring, not yet validated on GPUs)
+    ap.add_argument("--virtual-stages", type=int, default=int(os.environ.get("SKY_VIRTUAL_STAGES", "1")))
     ap.add_argument("--slow-rank", type=int, default=-1)
     ap.add_argument("--slowdown", type=float, default=0.0)
     return ap.parse_args()
@@ -164,11 +167,11 @@ def run_ours(args) -> dict:
                                                            intermediate=4096))
     allocator = sky.Allocator(model_config, wm, model_bench, dev_bench, granularity="block",
                               solver="exact" if args.alloc == "dynamic" else "heuristic")
-    wm = allocator.allocate(args.alloc)
+    wm = allocator.allocate(args.alloc, virtual_stages=args.virtual_stages if N > 1 else 1)
     layers_per_stage = [len(w.model_config) for w in wm.worker_pool]
 
     model = sky.RpcModel(wm, this_rank=rank)
-    optimizer = sky.build_optimizer(model.local_stage, dict(optim_type="SGD", lr=1e-3))
+    optimizer = sky.build_optimizer(model.optim_module, dict(optim_type="SGD", lr=1e-3))
     runner = sky.Runner(model=model, parameter_server=None, worker_manager=wm, optimizer=optimizer,
                         max_epochs=1, max_iters=10 ** 9, loss_cfg=dict(type="CrossEntropyLoss"),
                         timer_cfg=dict(root=log_root), logging_cfg=None,
@@ -265,6 +268,7 @@ def run_ours(args) -> dict:
                 "global_batch": global_batch, "seq_len": SEQ_LEN,
                 "parallelism": f"pp{N}" if N > 1 else "single-gpu",
                 "micro_batches": micro_batches, "schedule": eng.schedule,
+                "virtual_stages": getattr(model, "virtual_stages", 1),
                 "allocator": args.alloc, "layers_per_stage": layers_per_stage,
                 "boundary": ("fused-nvlink-p2p" if (eng.in_fused or eng.out_fused) else
                              ("none" if N == 1 else "nccl-p2p")),

@@ -166,7 +166,10 @@ class FusedBoundaryManager:
 
     def __init__(self, stage_index: int, num_stages: int, stage_to_rank: List[int],
                  micro_batches: int, rows: int, cols: int, mask_elems: int,
-                 device: torch.device, group=None):
+                 device: torch.device, group=None, ring: bool = False):
+        """``ring=True`` (looped pipelines): every stage has a previous and a next neighbour
+        (stage 0's previous is the last stage); ``micro_batches`` is then the number of slots,
+        one per (chunk, micro-batch)."""
         self.stage_index, self.num_stages = stage_index, num_stages
         self.stage_to_rank = stage_to_rank
         self.device = device
@@ -180,14 +183,18 @@ class FusedBoundaryManager:
         self._regions: List[BoundaryRegion] = []
         ext = nat.ext()
         has_prev, has_next = stage_index > 0, stage_index < num_stages - 1
+        if ring and num_stages > 1:
+            has_prev = has_next = True
+        prev_idx = (stage_index - 1) % num_stages
+        next_idx = (stage_index + 1) % num_stages
         my_rank = dist.get_rank(group)
         if has_prev:
-            ext.enable_peer_access(self._local_device_of(stage_to_rank[stage_index - 1]))
+            ext.enable_peer_access(self._local_device_of(stage_to_rank[prev_idx]))
             self.prev = FusedChannel(device, self.epoch_ptr, self.error_ptr)
             self.prev.local = BoundaryRegion(micro_batches, rows, cols, mask_elems, device)
             self._regions.append(self.prev.local)
         if has_next:
-            ext.enable_peer_access(self._local_device_of(stage_to_rank[stage_index + 1]))
+            ext.enable_peer_access(self._local_device_of(stage_to_rank[next_idx]))
             self.next = FusedChannel(device, self.epoch_ptr, self.error_ptr)
             self.next.local = BoundaryRegion(micro_batches, rows, cols, 0, device)
             self._regions.append(self.next.local)
@@ -208,12 +215,12 @@ class FusedBoundaryManager:
         dist.all_gather_object(gathered, mine, group=group)
         by_rank = {g["rank"]: g for g in gathered}
         if has_next:   # I write activations into next stage's "act" region
-            handle, lay = by_rank[stage_to_rank[stage_index + 1]]["act"]
+            handle, lay = by_rank[stage_to_rank[next_idx]]["act"]
             self.next.peer_base = ext.ipc_open(handle)
             self.next.peer_layout = lay
             self._opened.append(self.next.peer_base)
         if has_prev:   # I write gradients into prev stage's "grad" region
-            handle, lay = by_rank[stage_to_rank[stage_index - 1]]["grad"]
+            handle, lay = by_rank[stage_to_rank[prev_idx]]["grad"]
             self.prev.peer_base = ext.ipc_open(handle)
             self.prev.peer_layout = lay
             self._opened.append(self.prev.peer_base)

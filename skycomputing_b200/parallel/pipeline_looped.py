@@ -15,11 +15,14 @@ costs 1/v of a rank's work, so the step is ``m x T + (P - 1) x (F + B) / v`` as 
 easily for the models this framework targets.  Weight gradients use the same deferral as the
 plain engine.
 
-Transport in this version is ``torch.distributed`` point-to-point (gloo on CPU, NCCL on GPUs):
-both ends of a link post their transfers in the same (chunk, micro-batch) order, so plain FIFO
-matching is enough and no tags are needed.  The fused NVLink boundary (one slot per (chunk,
-micro-batch), ring channels incl. the wrap-around link) and CUDA-graph capture are the plain
-engine's and are not wired in here yet - see DESIGN.md §7.
+Transport: ``torch.distributed`` point-to-point by default (gloo on CPU, NCCL on GPUs) - both ends
+of a link post their transfers in the same (chunk, micro-batch) order, so plain FIFO matching is
+enough and no tags are needed.  ``boundary="fused"`` (``SKY_LOOPED_FUSED=1``) switches to the
+plain engine's peer-memory boundary: the ranks form a RING of ``FusedChannel``s (incl. the
+wrap-around link), one slot per (chunk, micro-batch), and the whole step is captured into one CUDA
+graph.  The p2p path is covered by the CPU tests (tests/test_pipeline_cpu.py); the fused path is
+written against the same kernels / flag protocol but has not been run on GPUs yet,
+which is why it is opt-in.
 """
 from __future__ import annotations
 
@@ -42,7 +45,7 @@ class LoopedPipelineEngine:
     def __init__(self, stages: Sequence, virtual_indices: Sequence[int], num_ranks: int,
                  ring: Sequence[int], device: torch.device, optimizer,
                  loss_fn: Optional[Callable] = None, micro_batches: int = 1, group=None,
-                 advance_rng: bool = True):
+                 advance_rng: bool = True, boundary: str = "dist", use_cuda_graph: bool = True):
         """``stages[i]`` is the ModuleWrapper of virtual stage ``virtual_indices[i]``; ``ring[p]`` is
         the process rank at ring position p (virtual stage k lives at position k % num_ranks)."""
         self.stages = list(stages)
@@ -53,6 +56,7 @@ class LoopedPipelineEngine:
         assert self.P >= 2, "a looped pipeline needs at least two ranks"
         assert self.vidx == sorted(self.vidx) and len(set(k % self.P for k in self.vidx)) == 1
         self.pos = self.vidx[0] % self.P
+        self.s = self.pos                                 # ring position (trace / log naming)
         assert self.vidx == [c * self.P + self.pos for c in range(self.v)], self.vidx
         self.ring = list(ring)
         self.device = device
@@ -79,6 +83,13 @@ class LoopedPipelineEngine:
         self._graph = None
         self._defer_wgrad = False
         self._setup_done = False
+        self.boundary = boundary
+        self._want_graph = use_cuda_graph and device.type == "cuda"
+        self.graphable = False
+        self._static_inputs: Optional[list] = None
+        self._static_labels: Optional[torch.Tensor] = None
+        self._eager_steps = 0
+        self.mb_batch = self.seq = 0
 
     # ------------------------------------------------------------------ helpers
     def _native_active(self) -> bool:
@@ -105,17 +116,123 @@ class LoopedPipelineEngine:
 
             flush_wgrads()
 
+    # ------------------------------------------------------------------ setup (collective)
+    def _setup(self, inputs) -> None:
+        self._loss_acc = torch.zeros((), dtype=torch.float32, device=self.device)
+        if self._native_active():
+            from ..ops.functions import set_wgrad_deferral
+
+            self._defer_wgrad = True
+            set_wgrad_deferral(True)
+        want_fused = self.boundary in ("auto", "fused") and self._native_active()
+        shape = [0, 0]
+        if self.is_first:
+            shape = [inputs[0].shape[0] // self.m, int(inputs[0].shape[1]) if inputs[0].dim() > 1 else 0]
+        box = [shape]
+        dist.broadcast_object_list(box, src=self.ring[0], group=self.group)
+        self.mb_batch, self.seq = box[0]
+        ok, hidden = False, 0
+        if want_fused:
+            ok = True
+            for c, st in enumerate(self.stages):
+                k = self.vidx[c]
+                in_ok, out_ok = st.fused_boundary_support()
+                ok = ok and (in_ok or k == 0) and (out_ok or k == self.total - 1)
+                spans = st.spans()
+                if spans:
+                    sp = spans[0]
+                    if sp.head is not None:
+                        hidden = sp.head.attention.output.dense.weight.shape[0]
+                        ok = ok and sp.head.attention.self.attention_head_size == 64
+            ok = ok and self.seq == 128 and hidden > 0 and hidden % 64 == 0 and \
+                (self.mb_batch * self.seq) % 128 == 0
+        flags = [None] * dist.get_world_size(self.group)
+        dist.all_gather_object(flags, (bool(ok), int(hidden)), group=self.group)
+        if want_fused and all(f[0] for f in flags):
+            from .p2p import FusedBoundaryManager
+
+            rows = self.mb_batch * self.seq
+            self.fused = FusedBoundaryManager(self.pos, self.P, self.ring, self.v * self.m, rows,
+                                              max(f[1] for f in flags), rows, self.device,
+                                              group=self.group, ring=True)
+            self.in_fused = self.out_fused = True
+            self.graphable = self._want_graph
+            if self.graphable:
+                for st in self.stages:
+                    st._record_forward_time = False
+                    st._logger = None
+        self._setup_done = True
+
+    def _fused_inputs(self, slot: int):
+        from ..ops import native as nat
+
+        ch = self.fused.prev
+        rows = self.mb_batch * self.seq
+        nat.ext().wait_flags(ch.local.mask_flag_ptr(slot), 1, ch.epoch_ptr, 1, ch.error_ptr,
+                             torch.cuda.current_stream().cuda_stream)
+        x = ch.act_view(slot, rows, ch.cols).view(self.mb_batch, self.seq, ch.cols)
+        x.requires_grad_(True)
+        mask = ch.mask_view(slot, rows).view(self.mb_batch, 1, 1, self.seq)
+        return (x, mask)
+
+    def _step_body_fused(self, inputs, labels) -> None:
+        """The same (chunk, micro-batch) order with every boundary in peer memory: no host-side
+        transfers at all, the kernels of neighbouring ranks hand panels to each other."""
+        from ..models.bert_layers import advance_rng
+
+        self.fused.advance_epoch()
+        if self._advance_rng:
+            advance_rng()
+        self._loss_acc.zero_()
+        chunks_in = [t.chunk(self.m, dim=0) for t in inputs] if self.is_first else None
+        label_chunks = labels.chunk(self.m, dim=0) if (self.is_last and labels is not None) else None
+        saved = {}
+        for kind, c, j in self._order:
+            k = self.vidx[c]
+            st = self.stages[c]
+            slot = c * self.m + j
+            first_stage, last_stage = k == 0, k == self.total - 1
+            st.microbatch = slot
+            st.in_channel = None if first_stage else self.fused.prev
+            st.out_channel = None if last_stage else self.fused.next
+            if kind == "F":
+                args = tuple(t[j] for t in chunks_in) if first_stage else self._fused_inputs(slot)
+                if not last_stage and not first_stage:
+                    self.fused.next.send_mask(args[-1], slot)   # the mask travels with the slot
+                outs = st(*args)
+                if not last_stage and first_stage:
+                    self.fused.next.send_mask(outs[-1], slot)   # produced by the embeddings here
+                loss = None
+                if last_stage:
+                    if hasattr(self.loss_fn, "fused"):
+                        loss = (self.loss_fn.fused(outs[0], label_chunks[j], 1.0 / self.m,
+                                                   self._loss_acc.view(1)),)
+                    else:
+                        loss = self.loss_fn(outs[0], label_chunks[j]) / self.m
+                        self._loss_acc += loss.detach().float()
+                saved[(c, j)] = (outs, loss)
+            else:
+                outs, loss = saved.pop((c, j))
+                self._flush_wgrads()
+                st.begin_backward()
+                if last_stage:
+                    if isinstance(loss, tuple):
+                        torch.autograd.backward([outs[0]], [loss[0].to(outs[0].dtype)])
+                    else:
+                        loss.backward()
+                else:
+                    torch.autograd.backward([outs[0]], [torch.zeros_like(outs[0])])
+                st.end_backward()
+        self._flush_wgrads()
+        self.optimizer.step()
+
     # ------------------------------------------------------------------ one optimisation step
     def train_step(self, inputs: Optional[Sequence[torch.Tensor]] = None,
                    labels: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         if not self._setup_done:
-            self._loss_acc = torch.zeros((), dtype=torch.float32, device=self.device)
-            if self._native_active():
-                from ..ops.functions import set_wgrad_deferral
-
-                self._defer_wgrad = True
-                set_wgrad_deferral(True)
-            self._setup_done = True
+            self._setup(inputs)
+        if self.fused is not None:
+            return self._train_step_fused(inputs, labels)
         if self._advance_rng and self._native_active():
             from ..models.bert_layers import advance_rng
 
@@ -176,6 +293,37 @@ class LoopedPipelineEngine:
         self._pending = []
         return self._loss_acc if self.is_last else None
 
+    def _train_step_fused(self, inputs, labels):
+        """Static buffers, 3 eager steps, then one CUDA graph per step (as in PipelineEngine)."""
+        out = self._loss_acc if self.is_last else None
+        if not self.graphable:
+            self._step_body_fused(inputs, labels)
+            return out
+        if self._static_inputs is None:
+            self._static_inputs = [t.clone() for t in inputs] if self.is_first else []
+            self._static_labels = labels.clone() if (self.is_last and labels is not None) else None
+        if self.is_first:
+            for s_, t in zip(self._static_inputs, inputs):
+                s_.copy_(t, non_blocking=True)
+        if self._static_labels is not None and labels is not None:
+            self._static_labels.copy_(labels, non_blocking=True)
+        if self._graph is None and self._eager_steps < 3:
+            self._step_body_fused(self._static_inputs, self._static_labels)
+            self._eager_steps += 1
+            return out
+        if self._graph is None:
+            from ..ops import native as nat
+
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            before = nat.launch_count()
+            with torch.cuda.graph(g):
+                self._step_body_fused(self._static_inputs, self._static_labels)
+            self.launches_per_step = nat.launch_count() - before
+            self._graph = g
+        self._graph.replay()
+        return out
+
     # ------------------------------------------------------------------ plain forward (eval)
     @torch.no_grad()
     def forward_only(self, inputs: Optional[Sequence[torch.Tensor]] = None):
@@ -197,6 +345,9 @@ class LoopedPipelineEngine:
     def close(self) -> None:
         if self.device.type == "cuda":
             torch.cuda.synchronize(self.device)
+        if self.fused is not None:
+            self.fused.close()
+            self.fused = None
         if self._defer_wgrad:
             from ..ops.functions import set_wgrad_deferral
 

@@ -123,7 +123,9 @@ class Runner:
             self.engine = LoopedPipelineEngine(
                 stages=model.local_stages, virtual_indices=model.local_stage_indices, num_ranks=P,
                 ring=model.stage_to_rank[:P], device=self.device, optimizer=self.optimizer,
-                loss_fn=self.loss_function, micro_batches=self.micro_batches)
+                loss_fn=self.loss_function, micro_batches=self.micro_batches,
+                boundary=("fused" if os.environ.get("SKY_LOOPED_FUSED", "0") == "1" else "dist"),
+                use_cuda_graph=self._use_cuda_graph)
             model.attach_engine(self.engine)
             return
         self.engine = PipelineEngine(
