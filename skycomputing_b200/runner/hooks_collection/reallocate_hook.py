@@ -31,7 +31,8 @@ def _dist():
 
 def _layout(worker_manager) -> list:
     """[(physical device, layer range)] in pipeline order."""
-    return [(w.device, tuple(w.layer_range) if w.layer_range is not None else None)
+    return [(w.device, tuple(map(tuple, w.chunks)) if getattr(w, "chunks", None)
+             else (tuple(w.layer_range) if w.layer_range is not None else None))
             for w in worker_manager.worker_pool]
 
 
@@ -76,7 +77,8 @@ class ReallocateHook(Hook):
         old_wm = runner.worker_manager
         new_wm = copy.deepcopy(old_wm)
         allocator = self._factory(new_wm)
-        new_wm = allocator.allocate(self._type)
+        v = max((len(w.chunks) for w in old_wm.worker_pool if getattr(w, "chunks", None)), default=1)
+        new_wm = allocator.allocate(self._type, virtual_stages=v)
         dev = allocator.last_device_times
         cost = allocator.last_layer_costs
         if not dev:  # "even" never benchmarks: nothing to compare
