@@ -37,13 +37,18 @@ def _layout(worker_manager) -> list:
 
 
 def _bottleneck(worker_manager, device_times: dict, layer_cost: list) -> float:
-    """max over stages of (device time) x (summed cost of its layers), spans in pool order."""
+    """max over workers of (device time) x (summed cost of the layers it runs)."""
     worst, pos = 0.0, 0
     for i, w in enumerate(worker_manager.worker_pool):
-        n = len(w.model_config)
+        if getattr(w, "chunks", None):
+            spans = list(w.chunks)
+        elif w.layer_range is not None:
+            spans = [tuple(w.layer_range)]
+        else:
+            spans = [(pos, pos + len(w.model_config))]
+        pos += len(w.model_config)
         t = device_times[w.device if w.device is not None else i]
-        worst = max(worst, t * sum(layer_cost[pos:pos + n]))
-        pos += n
+        worst = max(worst, t * sum(sum(layer_cost[b:e]) for b, e in spans))
     return worst
 
 
