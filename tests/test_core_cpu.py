@@ -305,3 +305,24 @@ def test_reference_named_helpers_exist_and_work(tmp_path):
     import pytest
     with pytest.raises(FileNotFoundError):
         fu.cached_path(str(tmp_path / "missing.bin"))
+
+
+def test_trace_tools_on_committed_timelines():
+    """tools/render_trace.py and tools/predict_schedule.py run on the committed 8-GPU traces and the
+    step-time model stays within 3 % of the measured span."""
+    import re
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    d = os.path.join(root, "profiles", "trace_n8_mb32")
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "render_trace.py"), "--dir", d,
+                          "--n", "8", "--res", "400"], capture_output=True, text=True, cwd=root)
+    assert out.returncode == 0, out.stderr
+    assert out.stdout.count("\ns") >= 7 and "F " in out.stdout
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "predict_schedule.py"), "--dir", d],
+                         capture_output=True, text=True, cwd=root)
+    assert out.returncode == 0, out.stderr
+    measured = float(re.search(r"measured step span\s+([0-9.]+)", out.stdout).group(1))
+    model = float(re.search(r"plain 1F1B model\s+([0-9.]+)", out.stdout).group(1))
+    assert abs(model - measured) / measured < 0.03
