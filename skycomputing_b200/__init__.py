@@ -10,6 +10,24 @@ def _ensure_core() -> None:
     """The C++ core (allocator / stimulator) is a hard dependency of `dynamics`; build it on first
     import if the in-tree .so is missing (g++ only, a few seconds).  The CUDA module is built by
     `__graft_entry__.build()` / `python -m skycomputing_b200._build` and is only needed on GPUs."""
+    import os
+    import sys
+
+    override = os.environ.get("SKY_CORE_OVERRIDE")
+    if override:
+        # an instrumented (ASAN / UBSAN) build of the core from tools/run_core_sanitizer.sh
+        import glob
+        import importlib.machinery
+        import importlib.util
+
+        path = glob.glob(os.path.join(override, "_core*.so"))[0]
+        loader = importlib.machinery.ExtensionFileLoader(__name__ + "._core", path)
+        spec = importlib.util.spec_from_loader(__name__ + "._core", loader)
+        mod = importlib.util.module_from_spec(spec)
+        loader.exec_module(mod)
+        sys.modules[__name__ + "._core"] = mod
+        globals()["_core"] = mod
+        return
     try:
         from . import _core  # noqa: F401
     except ImportError:
