@@ -199,3 +199,64 @@ def test_exact_solver_is_fast_for_paper_scale():
     even = _core.partition_bottleneck(lf, [1.0] * len(lf), t, [1e9] * 64, list(range(64)),
                                       _core.even_partition(len(lf), 64))
     assert r["bottleneck"] < even
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(2, 4), st.integers(2, 3), st.integers(0, 5),
+       st.lists(st.floats(0.5, 4.0), min_size=4, max_size=4))
+def test_looped_allocation_invariants(D, v, extra, speeds):
+    """v x D virtual stages: spans are contiguous in virtual-stage order, cover every layer exactly
+    once, none is empty, virtual stage k sits on worker k % D, and a faster device never gets less
+    work than a slower one placed on an identical cost profile."""
+    import skycomputing_b200 as sky
+
+    L = v * D + extra
+    cfg = [dict(layer_type="Linear", in_features=4, out_features=4) for _ in range(L)]
+
+    class DevB:
+        def __init__(self, wm):
+            self.wm = wm
+
+        def benchmark(self):
+            from skycomputing_b200.utils import generate_worker_name
+
+            return {generate_worker_name(w.rank): dict(time=speeds[w.device], avai_mem=1e9)
+                    for w in self.wm.worker_pool}
+
+    class ModB:
+        def benchmark(self):
+            return [1.0] * L, [1.0] * L
+
+    for alloc in ("even", "optimal"):
+        wm = sky.WorkerManager(first_rank=0)
+        wm.load_worker_pool_from_config([dict(name=f"w{i}", server_config={}, device=i,
+                                              extra_config={}) for i in range(D)])
+        a = sky.Allocator(cfg, wm, ModB(), DevB(wm), granularity="layer", solver="exact")
+        wm = a.allocate(alloc, virtual_stages=v)
+        spans = {}
+        for d, w in enumerate(wm.worker_pool):
+            assert w.device == d and len(w.chunks) == v
+            assert len(w.model_config) == sum(e - b for b, e in w.chunks)
+            for c, (b, e) in enumerate(w.chunks):
+                assert e > b
+                spans[c * D + d] = (b, e)
+        flat = [spans[k] for k in range(v * D)]
+        assert flat[0][0] == 0 and flat[-1][1] == L
+        assert all(flat[k][1] == flat[k + 1][0] for k in range(v * D - 1))
+        if alloc == "optimal":
+            worst = max(speeds[k % D] * (e - b) for k, (b, e) in enumerate(flat))
+            even = sky.Allocator(cfg, _fresh_pool(D), granularity="layer").allocate("even", virtual_stages=v)
+            ev = {}
+            for d, w in enumerate(even.worker_pool):
+                for c, (b, e) in enumerate(w.chunks):
+                    ev[c * D + d] = e - b
+            assert worst <= max(speeds[k % D] * ev[k] for k in range(v * D)) + 1e-9
+
+
+def _fresh_pool(D):
+    import skycomputing_b200 as sky
+
+    wm = sky.WorkerManager(first_rank=0)
+    wm.load_worker_pool_from_config([dict(name=f"w{i}", server_config={}, device=i, extra_config={})
+                                     for i in range(D)])
+    return wm

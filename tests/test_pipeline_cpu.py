@@ -319,7 +319,7 @@ def test_reallocate_hook_migrates_layers_without_changing_the_training_result(tm
 # ---------------------------------------------------------------------------------------------
 # Looped (virtual-stage) pipeline: v chunks per rank, ring of ranks
 # ---------------------------------------------------------------------------------------------
-def _train_looped(rank, world, virtual_stages, micro_batches, steps, tmp, alloc):
+def _train_looped(rank, world, virtual_stages, micro_batches, steps, tmp, alloc, save_to=None):
     cfg = _model_cfg(layers=4)
     wm = sky.WorkerManager(first_rank=0)
     wm.load_worker_pool_from_config([
@@ -337,10 +337,14 @@ def _train_looped(rank, world, virtual_stages, micro_batches, steps, tmp, alloc)
         if mod.is_local:
             _seed_layers(mod.module, mod.layer_range[0])
     opt = sky.build_optimizer(model.optim_module, dict(optim_type="SGD", lr=0.1))
-    runner = sky.Runner(model=model, parameter_server=None, worker_manager=wm, optimizer=opt,
+    ps = sky.ParameterServer(cfg, lazy=True) if (rank == 0 and save_to) else None
+    runner = sky.Runner(model=model, parameter_server=ps, worker_manager=wm, optimizer=opt,
                         max_epochs=1, max_iters=steps, loss_cfg=dict(type="CrossEntropyLoss"),
                         timer_cfg=dict(root=tmp), logging_cfg=None, micro_batches=micro_batches,
                         schedule="1f1b" if micro_batches > 1 else "sequential")
+    if save_to:
+        runner.register_hook(sky.CheckpointHook(save_path=save_to, save_interval=1,
+                                                save_optimizer=False))
     dl = sky.build_dataloader_from_cfg(
         dataset_cfg=dict(type="SynthMNLIDataset", num_samples=8 * steps, max_seq_length=16,
                          vocab_size=100, seed=5),
@@ -415,3 +419,18 @@ def test_launcher_looped_pipeline_from_config(tmp_path):
     d = os.path.join(str(tmp_path), "logs", "3nodes_4layers", "even")
     log = open(os.path.join(d, "allocation.log")).read()
     assert "runs layer spans [(0, 4), (10, 14)]" in log and log.count("step time") == 2
+
+
+def test_checkpoint_of_a_looped_pipeline_equals_plain_checkpoint(tmp_path):
+    """Layer-indexed checkpoints do not care that a rank owns several non-adjacent chunks."""
+    tmp = str(tmp_path)
+    a_dir, b_dir = os.path.join(tmp, "looped"), os.path.join(tmp, "plain")
+    run_distributed(_train_looped, 2, 2, 2, 3, tmp, "even", a_dir)
+    run_distributed(_train_looped, 2, 1, 2, 3, tmp, "even", b_dir)
+    fa = [f for f in os.listdir(a_dir) if f.endswith(".pth") and ".extra." not in f]
+    fb = [f for f in os.listdir(b_dir) if f.endswith(".pth") and ".extra." not in f]
+    assert fa and fa == fb
+    sa, sb = torch.load(os.path.join(a_dir, fa[0])), torch.load(os.path.join(b_dir, fb[0]))
+    assert sorted(sa) == sorted(sb) and any(k.startswith("14.") for k in sa)
+    for k in sa:
+        assert torch.allclose(sa[k].float(), sb[k].float(), rtol=1e-5, atol=1e-7), k
