@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--schedule", default="1f1b")
     ap.add_argument("--dropout", type=float, default=0.0)
     ap.add_argument("--tag", default="")
+    # > 1: looped pipeline (v chunks per GPU); add SKY_LOOPED_FUSED=1 for its fused ring boundary.
+    # The loss trajectory must equal the plain pipeline's (same seeds per GLOBAL layer index).
+    ap.add_argument("--virtual-stages", type=int, default=1)
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -50,19 +53,23 @@ def main():
                for i in range(world)]
     wm = sky.WorkerManager(first_rank=0)
     wm.load_worker_pool_from_config(workers)
-    wm = sky.Allocator(model_config, wm, granularity="block").even_allocate()
+    wm = sky.Allocator(model_config, wm, granularity="block").allocate(
+        "even", virtual_stages=a.virtual_stages)
     # identical initial weights regardless of the partition: seed per GLOBAL layer index
     model = sky.RpcModel(wm, this_rank=rank)
-    b0 = model.local_module.layer_range[0]
-    for off, layer in enumerate(model.local_stage.layers.children()):
-        g = torch.Generator(device="cpu").manual_seed(1000 + b0 + off)
-        with torch.no_grad():
-            for p in layer.parameters():
-                p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.device))
-            for n, p in layer.named_parameters():
-                if n.endswith("LayerNorm.weight"):
-                    p.fill_(1.0)
-    opt = sky.build_optimizer(model.local_stage, dict(optim_type="SGD", lr=0.01))
+    for mod in model.model:
+        if not mod.is_local:
+            continue
+        b0 = mod.layer_range[0]
+        for off, layer in enumerate(mod.module.layers.children()):
+            g = torch.Generator(device="cpu").manual_seed(1000 + b0 + off)
+            with torch.no_grad():
+                for p in layer.parameters():
+                    p.copy_((torch.randn(p.shape, generator=g) * 0.02).to(p.device))
+                for n, p in layer.named_parameters():
+                    if n.endswith("LayerNorm.weight"):
+                        p.fill_(1.0)
+    opt = sky.build_optimizer(model.optim_module, dict(optim_type="SGD", lr=0.01))
     runner = sky.Runner(model=model, parameter_server=None, worker_manager=wm, optimizer=opt,
                         max_epochs=1, max_iters=10 ** 9, loss_cfg=dict(type="CrossEntropyLoss"),
                         timer_cfg=dict(root="/tmp/sky_check"), logging_cfg=None,
@@ -79,7 +86,8 @@ def main():
             losses.append(round(out, 5))
     torch.cuda.synchronize()
     eng = runner.engine
-    info = dict(tag=a.tag, world=world, boundary=a.boundary, fused=(eng.in_fused or eng.out_fused),
+    info = dict(tag=a.tag, world=world, boundary=a.boundary, schedule=eng.schedule,
+                virtual_stages=a.virtual_stages, fused=(eng.in_fused or eng.out_fused),
                 graph=eng._graph is not None, mb=a.micro_batches, losses=losses,
                 err=eng.fused.error_code() if eng.fused is not None else 0)
     gathered = [None] * world
