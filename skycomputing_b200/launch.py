@@ -86,7 +86,15 @@ def run_process(rank: int, world_size: int, rpc_config: dict, model_config: list
         backend = "nccl" if use_cuda else "gloo"
     print("starting to initialize the process group on rank: {} ({})".format(rank, backend), flush=True)
     if not dist.is_initialized():
-        kwargs = dict(backend=backend, rank=rank, world_size=world_size)
+        # failure detection for the un-fused (NCCL) boundaries: a peer that died or hung turns into
+        # an exception on the survivors after the timeout instead of a silent stall (the fused
+        # boundaries have their own in-kernel 4 s flag timeouts, Runner._check_boundary_health)
+        os.environ.setdefault("TORCH_NCCL_ASYNC_ERROR_HANDLING", "1")
+        import datetime
+
+        timeout_s = int(rpc_config.get("rpc_timeout", 1200)) if isinstance(rpc_config, dict) else 1200
+        kwargs = dict(backend=backend, rank=rank, world_size=world_size,
+                      timeout=datetime.timedelta(seconds=timeout_s))
         if use_cuda:
             kwargs["device_id"] = device
         dist.init_process_group(**kwargs)
