@@ -68,7 +68,7 @@ class LoopedPipelineEngine:
         self.next_rank = self.ring[(self.pos + 1) % self.P]
         self.is_first = self.vidx[0] == 0                 # owns the stage that reads the data
         self.is_last = self.vidx[-1] == self.total - 1    # owns the stage that computes the loss
-        self.comm = TorchDistComm(device, group=group)
+        self._comm: Optional[TorchDistComm] = None       # created on first use (p2p path only)
         self._loss_acc: Optional[torch.Tensor] = None
         self._advance_rng = advance_rng
         self._pending: list = []
@@ -92,6 +92,12 @@ class LoopedPipelineEngine:
         self.mb_batch = self.seq = 0
 
     # ------------------------------------------------------------------ helpers
+    @property
+    def comm(self) -> TorchDistComm:
+        if self._comm is None:
+            self._comm = TorchDistComm(self.device, group=self.group)
+        return self._comm
+
     def _native_active(self) -> bool:
         from ..models.bert_layers import get_backend
         from ..ops import native as nat

@@ -100,3 +100,74 @@ def test_fused_sgd_marks_only_wgrad_targets(monkeypatch):
     assert w.fresh and not b.fresh
     opt.zero_grad()
     assert not w.fresh
+
+
+def test_looped_fused_step_body_order_and_slots(monkeypatch):
+    """The (GPU-only) fused step body of the looped engine, driven with fakes on CPU: breadth-first
+    order, slot = chunk * m + micro-batch, masks relayed once per slot, first / last virtual stage
+    special cases, one optimizer step."""
+    from skycomputing_b200.parallel.pipeline_looped import LoopedPipelineEngine
+
+    log = []
+
+    class Stage(torch.nn.Module):
+        def __init__(self, name):
+            super().__init__()
+            self.name = name
+            self.w = torch.nn.Parameter(torch.ones(()))
+
+        def forward(self, *args):
+            log.append(("F", self.name, self.microbatch, self.in_channel is not None,
+                        self.out_channel is not None))
+            x = args[0].float() * self.w
+            return (x, args[-1])
+
+        def begin_backward(self):
+            log.append(("B", self.name, self.microbatch))
+
+        def end_backward(self):
+            pass
+
+    class Chan:
+        def __init__(self, name):
+            self.name = name
+
+        def send_mask(self, mask, slot):
+            log.append(("mask", self.name, slot))
+
+    class Fused:
+        prev, next = Chan("prev"), Chan("next")
+
+        def advance_epoch(self):
+            log.append(("epoch",))
+
+    class Opt:
+        def step(self):
+            log.append(("opt",))
+
+    P, v, m = 2, 2, 2
+    for pos in (0, 1):
+        log.clear()
+        stages = [Stage(f"c{c}") for c in range(v)]
+        eng = LoopedPipelineEngine(stages, [c * P + pos for c in range(v)], P, [0, 1],
+                                   torch.device("cpu"), Opt(),
+                                   loss_fn=lambda out, lab: out.mean(), micro_batches=m,
+                                   advance_rng=False)
+        eng.fused, eng._setup_done = Fused(), True
+        eng._loss_acc = torch.zeros(())
+        monkeypatch.setattr(eng, "_fused_inputs",
+                            lambda slot: (torch.ones(2, 3, requires_grad=True), torch.zeros(2)))
+        data = [torch.ones(4, 3, requires_grad=True), torch.zeros(4)]
+        eng._step_body_fused(data if pos == 0 else None, torch.zeros(4) if pos == 1 else None)
+        fwd = [e for e in log if e[0] == "F"]
+        assert [(e[1], e[2]) for e in fwd] == [("c0", 0), ("c0", 1), ("c1", 2), ("c1", 3)]
+        bwd = [e for e in log if e[0] == "B"]
+        assert [(e[1], e[2]) for e in bwd] == [("c1", 2), ("c1", 3), ("c0", 0), ("c0", 1)]
+        # virtual stage 0 has no inbound channel, the last one no outbound channel
+        assert fwd[0][3] == (pos != 0) and fwd[-1][4] == (pos != 1)
+        masks = [e for e in log if e[0] == "mask"]
+        assert all(e[1] == "next" for e in masks)
+        assert sorted(e[2] for e in masks) == ([0, 1, 2, 3] if pos == 0 else [0, 1])
+        assert log[0] == ("epoch",) and log[-1] == ("opt",) and log.count(("opt",)) == 1
+        if pos == 1:
+            assert float(eng._loss_acc) > 0
