@@ -48,8 +48,12 @@ class Allocator:
     def __init__(self, model_cfg: list, worker_manager: WorkerManager, model_benchmarker=None,
                  device_benchmarker=None, solver: str = "heuristic", granularity: str = "layer",
                  comm_aware: bool = False, boundary_bytes: Optional[Sequence[float]] = None,
-                 link_bytes_per_s: float = 770e9, device_flops_per_s: float = 7e14,
+                 link_bytes_per_s: float = 340e9, device_flops_per_s: float = 7e14,
                  logger=None):
+        # comm_aware cost of a cut = boundary bytes / link_bytes_per_s.  340 GB/s is what the fused
+        # boundary kernels (and NCCL p2p) actually sustain for the 4-8 MiB stage-boundary tensors
+        # on NVLink 5 (profiles/boundary_roofline.md), not the 900 GB/s line rate;
+        # device_flops_per_s is the sustained rate of a transformer block on one B200.
         assert solver in ("heuristic", "compat", "exact"), solver
         assert granularity in ("layer", "block"), granularity
         self._model_cfg = model_cfg
