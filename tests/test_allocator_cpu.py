@@ -260,3 +260,31 @@ def _fresh_pool(D):
     wm.load_worker_pool_from_config([dict(name=f"w{i}", server_config={}, device=i, extra_config={})
                                      for i in range(D)])
     return wm
+
+
+def test_schedule_planner_reproduces_measured_steps_and_ranks_plans():
+    """Closed-form step model vs the measured 8 / 4 / 2-GPU steps (profiles/bench_history.md), and
+    the ordering of plans it implies."""
+    import skycomputing_b200 as sky
+
+    # per-micro-batch costs of a 3-block stage at 32 sequences, from the committed 8-GPU timeline
+    c8 = sky.StageCosts(forward=0.527e-3, backward=0.977e-3, period=1.516e-3)
+    p8 = sky.SchedulePlanner(8, c8, blocks_per_stage=3)
+    assert p8.step_time(32, 8) == pytest.approx(22.76e-3, rel=0.02)      # measured 22.76 ms
+    assert p8.step_time(16, 16) == pytest.approx(23.30e-3, rel=0.05)     # measured 23.30 ms
+    assert p8.step_time(8, 32) > 1.4 * p8.step_time(16, 16)              # measured 43.5 vs 30.9 ms
+    best = p8.best(256)
+    assert best.schedule == "looped" and best.virtual_stages == 3 and best.micro_batch == 32
+    assert best.step_seconds < 0.75 * p8.step_time(32, 8)
+    plain = p8.best(256, allow_looped=False)
+    assert plain.virtual_stages == 1 and plain.micro_batch in (16, 32)
+    # derived from the measured single-GPU step (11.72 ms for 32 sequences): 2 and 4 GPUs
+    p2 = sky.SchedulePlanner(2, sky.costs_from_single_gpu_step(11.72e-3, 2), blocks_per_stage=12)
+    assert p2.step_time(32, 2) == pytest.approx(17.62e-3, rel=0.05)      # measured 17.62 ms
+    assert p2.step_time(16, 4) == pytest.approx(18.27e-3, rel=0.08)      # measured 18.27 ms
+    p4 = sky.SchedulePlanner(4, sky.costs_from_single_gpu_step(11.72e-3, 4), blocks_per_stage=6)
+    assert p4.step_time(16, 8) == pytest.approx(19.92e-3, rel=0.08)      # measured 19.92 ms
+    assert p4.best(128).schedule == "looped"
+    # one GPU: no pipeline terms, no looped candidates
+    p1 = sky.SchedulePlanner(1, sky.costs_from_single_gpu_step(11.72e-3, 1), blocks_per_stage=24)
+    assert p1.best(32).virtual_stages == 1 and p1.step_time(32, 1) == pytest.approx(11.72e-3)
