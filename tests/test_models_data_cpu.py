@@ -219,3 +219,37 @@ def test_hook_base_helpers():
     for name in ("before_run", "after_run", "before_train_epoch", "after_train_epoch",
                  "before_train_iter", "after_train_iter", "before_val_epoch", "after_val_iter"):
         getattr(h, name)(R)                                              # all no-ops by default
+
+
+def test_span_fusion_plan_and_boundary_support(tmp_path):
+    """ModuleWrapper groups consecutive Head / Body / Tail entries into fused spans (one autograd
+    node, one kernel chain) whatever sub-block cut the allocator chose, and reports which sides of
+    the stage can use the fused NVLink boundary (whole-block cuts only)."""
+    from skycomputing_b200.models.bert_layers import BertSpan
+
+    c = sky.BertConfig(50, hidden_size=32, num_hidden_layers=2, num_attention_heads=4,
+                       intermediate_size=64, max_position_embeddings=16)
+    L = lambda t: dict(layer_type=t, config=c.__dict__)  # noqa: E731
+    H, B, T = L("BertLayer_Head"), L("BertLayer_Body"), L("BertLayer_Tail")
+    tail_cls = [L("BertPooler"), dict(layer_type="BertTailForClassification", hidden_dropout_prob=0.0,
+                                      hidden_size=32, num_classes=3)]
+
+    def shape(cfgs):
+        mw = sky.build_module_from_cfg(0, cfgs, dict(timer_config=dict(root=str(tmp_path))))
+        plan = mw._build_plan()
+        desc = []
+        for s in plan:
+            if isinstance(s, BertSpan):
+                desc.append("".join(n for n, x in (("H", s.head), ("B", s.body), ("T", s.tail))
+                                    if x is not None))
+            else:
+                desc.append(type(s).__name__)
+        return desc, mw.fused_boundary_support(), len(mw.spans())
+
+    assert shape([L("BertEmbeddings"), H, B, T, H, B, T] + tail_cls) == (
+        ["BertEmbeddings", "HBT", "HBT", "BertPooler", "BertTailForClassification"], (False, False), 2)
+    assert shape([H, B, T, H, B, T]) == (["HBT", "HBT"], (True, True), 2)       # middle stage
+    assert shape([B, T, H, B]) == (["BT", "HB"], (False, False), 2)             # sub-block cuts
+    assert shape([T, H]) == (["T", "H"], (False, False), 2)
+    assert shape([H, B, T] + tail_cls)[1] == (True, False)                       # last stage
+    assert shape([L("BertEmbeddings"), H, B, T])[1] == (False, True)             # first stage
