@@ -37,6 +37,10 @@ namespace sky {
 
 namespace {
 
+#ifndef SKY_GEMM_SETMAXNREG
+#define SKY_GEMM_SETMAXNREG 0
+#endif
+
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle-128B row
 constexpr int UMMA_K = 16;
@@ -228,6 +232,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   pdl_wait();
   pdl_launch_dependents();
 
+  // Optional register re-allocation between the warpgroups (setmaxnreg): the producer / MMA /
+  // allocator warpgroup keeps 40 registers per thread, the two epilogue warpgroups get 232 (the
+  // launch allocation is 384 x 168).  Compile-time experiment, OFF by default: with it ptxas
+  // removes the 48-68 byte spill frames of the 256-wide instantiations, but it has not been run
+  // on a GPU yet (build with SKY_GEMM_SETMAXNREG=1 in the environment to try it).
+#if SKY_GEMM_SETMAXNREG
+  if (warp_idx < 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+#endif
   if (warp_idx == 0) {
     // ===================================== TMA producer =====================================
     int stage = 0;
@@ -376,7 +389,14 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
         }
       }
     }
+#if SKY_GEMM_SETMAXNREG
+  }
+  } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    {
+#else
   } else if (warp_idx >= kEpiWarp0) {
+#endif
     // ====================================== epilogue =======================================
     // 8 warps: warp e handles TMEM lane quadrant (e & 3) and column half (e >> 2) of the tile.
     // Latency hiding (profiles/gemm_epilogue_v1.md: the first version stalled ~80% on
@@ -660,6 +680,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
       }
     }
   }
+
+#if SKY_GEMM_SETMAXNREG
+  }
+#endif
 
   tcgen05_fence_before();
   __syncwarp();

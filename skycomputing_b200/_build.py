@@ -44,6 +44,10 @@ NVCC_FLAGS = [
     "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
 ]
+# compile-time experiments (off by default; the content hash covers the flags, so flipping one
+# rebuilds): SKY_GEMM_SETMAXNREG=1 -> register re-allocation between the GEMM's warpgroups
+if os.environ.get("SKY_GEMM_SETMAXNREG", "0") == "1":
+    NVCC_FLAGS.append("-DSKY_GEMM_SETMAXNREG=1")
 CXX_FLAGS = ["-O2", "-std=c++17", "-fPIC", "-fvisibility=hidden", "-Wall"]
 
 
