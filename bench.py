@@ -49,9 +49,9 @@ def parse_args():
     ap.add_argument("--boundary", type=str, default=os.environ.get("SKY_BOUNDARY", "auto"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--layers", type=int, default=LAYER_NUM)
-    # > 1: looped pipeline, v non-adjacent chunks per GPU (parallel/pipeline_looped.py); torch.
-    # distributed boundaries unless SKY_LOOPED_FUSED=1 (fused ring, not yet validated on GPUs)
-    ap.add_argument("--virtual-stages", type=int, default=int(os.environ.get("SKY_VIRTUAL_STAGES", "1")))
+    # > 1: looped pipeline, v non-adjacent chunks per GPU on a ring of fused NVLink boundaries
+    # (parallel/pipeline_looped.py); 0 = let the SchedulePlanner pick (micro-batch, count, v)
+    ap.add_argument("--virtual-stages", type=int, default=int(os.environ.get("SKY_VIRTUAL_STAGES", "0")))
     ap.add_argument("--slow-rank", type=int, default=-1)
     ap.add_argument("--slowdown", type=float, default=0.0)
     return ap.parse_args()
@@ -118,22 +118,68 @@ def run_ours(args) -> dict:
     os.environ.setdefault("MASTER_PORT", "29533")
     dist.init_process_group(backend="nccl", rank=rank, world_size=world, device_id=device)
 
-    import skycomputing_b200 as sky
-    from skycomputing_b200.models import BertConfig, set_backend
+    from skycomputing_b200.models import set_backend
     from skycomputing_b200.ops import native as nat
 
     assert nat.available(), "sm_100a extension missing: run __graft_entry__.build()"
     set_backend("native")
     nat.enable_launch_counter()
-    torch.manual_seed(1234)
+
+    plan = pick_plan(args)
+    result = measure(args, plan, rank, world, local_rank, device)
+    if result == "fallback":
+        # the planned schedule did not survive its warm-up (flag-wait error / non-finite loss on
+        # some rank): measure the plain 1F1B pipeline instead and say so
+        plain = dict(plan, virtual_stages=1, micro_batch=(BATCH_PER_GPU if args.gpus <= 2 else 16),
+                     note="fallback from " + plan["schedule"])
+        plain["micro_batches"] = BATCH_PER_GPU * args.gpus // plain["micro_batch"]
+        plain["schedule"] = "1f1b"
+        result = measure(args, plain, rank, world, local_rank, device)
+        if result == "fallback":
+            result = None
+    dist.destroy_process_group()
+    return result
+
+
+def pick_plan(args) -> dict:
+    """(micro-batch size, micro-batch count, virtual stages) for this GPU count.
+
+    The SchedulePlanner's closed-form step model (dynamics/planner.py; it reproduced every measured
+    multi-GPU step of round 1 within 2-8 %) ranks the candidates; per-stage costs are derived from
+    the single-GPU step of the same per-GPU batch.  Flags / environment override the plan."""
+    from skycomputing_b200.dynamics.planner import SchedulePlanner, costs_from_single_gpu_step
 
     N = args.gpus
     global_batch = BATCH_PER_GPU * N
-    # micro-batch size: 32-sequence GEMMs run ~25 % more efficiently than 16-sequence ones, the
-    # 1F1B bubble shrinks with more micro-batches; measured cross-over between N=2 and N=4
-    # (profiles/bench_history.md)
-    mb = args.micro_batch or (BATCH_PER_GPU if N <= 2 else 16)
-    micro_batches = max(1, global_batch // mb)
+    blocks_per_stage = max(1, args.layers // N)
+    single_gpu_step = 11.7e-3 * args.layers / 24.0      # measured: BENCH_r01 (32 sequences)
+    planner = SchedulePlanner(N, costs_from_single_gpu_step(single_gpu_step, N), blocks_per_stage)
+    sizes = (args.micro_batch,) if args.micro_batch else (16, 32)
+    cands = planner.candidates(global_batch, micro_batch_sizes=sizes, allow_looped=N > 1)
+    if args.virtual_stages > 0:
+        cands = [c for c in cands if c.virtual_stages == args.virtual_stages] or cands
+    # a looped pipeline needs at least as many micro-batches as ranks to keep the ring full
+    cands = [c for c in cands if c.virtual_stages == 1 or c.micro_batches >= min(N, 2)] or cands
+    best = cands[0]
+    return dict(micro_batch=best.micro_batch, micro_batches=best.micro_batches,
+                virtual_stages=best.virtual_stages if N > 1 else 1, schedule=best.schedule,
+                predicted_ms=round(best.step_seconds * 1e3, 3))
+
+
+def measure(args, plan, rank, world, local_rank, device):
+    import torch
+    import torch.distributed as dist
+
+    import skycomputing_b200 as sky
+    from skycomputing_b200.models import BertConfig
+    from skycomputing_b200.ops import native as nat
+
+    torch.manual_seed(1234)
+    N = args.gpus
+    global_batch = BATCH_PER_GPU * N
+    mb = plan["micro_batch"]
+    micro_batches = plan["micro_batches"]
+    virtual_stages = plan["virtual_stages"]
     cfg = BertConfig.bert_large()
     encoder = [dict(layer_type="BertLayer_Head", config=cfg.__dict__),
                dict(layer_type="BertLayer_Body", config=cfg.__dict__),
@@ -165,9 +211,11 @@ def run_ours(args) -> dict:
                                           proxy="bert_block",
                                           block_shape=dict(tokens=mb * SEQ_LEN, hidden=1024,
                                                            intermediate=4096))
+    # `dynamic` = the greedy boundary-shifting solver (the reference's algorithm with its dead
+    # shrink branch fixed), `optimal` = the exact min-max partition
     allocator = sky.Allocator(model_config, wm, model_bench, dev_bench, granularity="block",
-                              solver="exact" if args.alloc == "dynamic" else "heuristic")
-    wm = allocator.allocate(args.alloc, virtual_stages=args.virtual_stages if N > 1 else 1)
+                              solver="heuristic")
+    wm = allocator.allocate(args.alloc, virtual_stages=virtual_stages if N > 1 else 1)
     layers_per_stage = [len(w.model_config) for w in wm.worker_pool]
 
     model = sky.RpcModel(wm, this_rank=rank)
@@ -200,10 +248,29 @@ def run_ours(args) -> dict:
 
     # ---------------- device-timed region (inputs resident on the device) ----------------
     n_untimed = max(args.warmup, 5)  # >= 3 eager steps + graph capture happen in here
+    warm_loss = None
     for i in range(n_untimed):
         d, l = dev_batches[i % 4]
-        eng.train_step(d if eng.is_first else None, l if eng.is_last else None)
+        warm_loss = eng.train_step(d if eng.is_first else None, l if eng.is_last else None)
     barrier_sync()
+    # health check of the schedule before anything is timed (all ranks agree on the verdict)
+    bad = 0
+    if eng.fused is not None and eng.fused.error_code():
+        bad = 1
+    if warm_loss is not None and not bool(torch.isfinite(warm_loss).all()):
+        bad = 1
+    if world > 1:
+        bt = torch.tensor([bad], device=device)
+        dist.all_reduce(bt, op=dist.ReduceOp.MAX)
+        bad = int(bt.item())
+    if bad:
+        if rank == 0:
+            print(f"[bench] plan {plan} failed its warm-up (flag error / non-finite loss)",
+                  file=sys.stderr, flush=True)
+        eng.close()
+        del runner, model, optimizer, eng
+        torch.cuda.empty_cache()
+        return "fallback"
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
@@ -254,6 +321,7 @@ def run_ours(args) -> dict:
     if os.environ.get("SKY_TRACE", "0") == "1":
         _dump_trace(eng, rank, world, device, N)
     result = None
+    n_params_m = 31.8 + 12.596 * args.layers + 1.05
     if rank == 0:
         value = global_batch * args.steps / (dev_ms * 1e-3)
         e2e = global_batch * args.steps / (e2e_ms * 1e-3)
@@ -264,12 +332,13 @@ def run_ours(args) -> dict:
             "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "impl": "ours",
             "data": "synthetic MNLI-shaped (random ids, seq 128), random-init weights",
             "config": {
-                "model": f"BERT-large L={args.layers} H=1024 A=16 I=4096 (335M params)",
+                "model": f"BERT-large L={args.layers} H=1024 A=16 I=4096 ({n_params_m:.0f}M params)",
                 "global_batch": global_batch, "seq_len": SEQ_LEN,
                 "parallelism": f"pp{N}" if N > 1 else "single-gpu",
                 "micro_batches": micro_batches, "schedule": eng.schedule,
                 "virtual_stages": getattr(model, "virtual_stages", 1),
                 "allocator": args.alloc, "layers_per_stage": layers_per_stage,
+                "plan": plan,
                 "boundary": ("fused-nvlink-p2p" if (eng.in_fused or eng.out_fused) else
                              ("none" if N == 1 else "nccl-p2p")),
                 "cuda_graph": eng._graph is not None, "optimizer": "fused SGD lr=1e-3, fp32 master weights",
@@ -287,7 +356,6 @@ def run_ours(args) -> dict:
             "flag_wait_errors": err,
         }
     eng.close()
-    dist.destroy_process_group()
     return result
 
 

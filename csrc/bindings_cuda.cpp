@@ -261,7 +261,8 @@ void softmax_ce(uintptr_t logits, uintptr_t labels, uintptr_t loss, uintptr_t dl
 
 // descriptors: list of (p, g, mom, p_bf16, numel) -> packed host bytes to upload once
 py::bytes pack_sgd_descriptors(
-    const std::vector<std::tuple<uintptr_t, uintptr_t, uintptr_t, uintptr_t, long long, int>>& ts) {
+    const std::vector<std::tuple<uintptr_t, uintptr_t, uintptr_t, uintptr_t, long long, int,
+                                 uintptr_t>>& ts) {
   std::vector<sky::SgdTensor> v(ts.size());
   for (size_t i = 0; i < ts.size(); ++i) {
     v[i].p = P<float>(std::get<0>(ts[i]));
@@ -271,6 +272,7 @@ py::bytes pack_sgd_descriptors(
     v[i].numel = std::get<4>(ts[i]);
     v[i].skip_zero = std::get<5>(ts[i]);
     v[i].pad_ = 0;
+    v[i].mom2 = P<float>(std::get<6>(ts[i]));
   }
   return py::bytes(reinterpret_cast<const char*>(v.data()), v.size() * sizeof(sky::SgdTensor));
 }
@@ -279,6 +281,14 @@ void sgd_multi(uintptr_t d_tensors, int n, long long max_numel, float lr, float 
   check(sky::launch_sgd_multi(P<const sky::SgdTensor>(d_tensors), n, max_numel, lr, momentum,
                               weight_decay, grad_scale, zero_grad, S(stream)),
         "sgd_multi");
+}
+void adam_multi(uintptr_t d_tensors, int n, long long max_numel, float lr, float beta1, float beta2,
+                float eps, float weight_decay, bool decoupled, uintptr_t step, float grad_scale,
+                bool zero_grad, uintptr_t stream) {
+  check(sky::launch_adam_multi(P<const sky::SgdTensor>(d_tensors), n, max_numel, lr, beta1, beta2,
+                               eps, weight_decay, decoupled, P<const uint64_t>(step), grad_scale,
+                               zero_grad, S(stream)),
+        "adam_multi");
 }
 void cast_f32_to_bf16(uintptr_t src, uintptr_t dst, long long n, uintptr_t stream) {
   check(sky::launch_cast_f32_to_bf16(P<const float>(src), P<void>(dst), n, S(stream)), "cast");
@@ -427,6 +437,10 @@ PYBIND11_MODULE(_cuda, m) {
   m.def("pack_sgd_descriptors", &pack_sgd_descriptors);
   m.def("sgd_multi", &sgd_multi, py::arg("d_tensors"), py::arg("n"), py::arg("max_numel"),
         py::arg("lr"), py::arg("momentum") = 0.f, py::arg("weight_decay") = 0.f,
+        py::arg("grad_scale") = 1.f, py::arg("zero_grad") = true, py::arg("stream") = 0);
+  m.def("adam_multi", &adam_multi, py::arg("d_tensors"), py::arg("n"), py::arg("max_numel"),
+        py::arg("lr"), py::arg("beta1") = 0.9f, py::arg("beta2") = 0.999f, py::arg("eps") = 1e-8f,
+        py::arg("weight_decay") = 0.f, py::arg("decoupled") = false, py::arg("step") = 0,
         py::arg("grad_scale") = 1.f, py::arg("zero_grad") = true, py::arg("stream") = 0);
   m.def("cast_f32_to_bf16", &cast_f32_to_bf16);
   m.def("cast_bf16_to_f32", &cast_bf16_to_f32);

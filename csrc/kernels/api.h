@@ -215,10 +215,17 @@ struct SgdTensor {
   long long numel;
   int skip_zero;      // the first gradient write of the next step OVERWRITES g: do not zero it
   int pad_;
+  float* mom2;        // Adam second moment (null for SGD)
 };
 int launch_sgd_multi(const SgdTensor* d_tensors, int n_tensors, long long max_numel, float lr,
                      float momentum, float weight_decay, float grad_scale, bool zero_grad,
                      cudaStream_t stream);
+// Multi-tensor fused Adam / AdamW (torch.optim.Adam(W) semantics, amsgrad=False): moments in
+// `mom` / `mom2`, the step count lives in DEVICE memory (`step`, advanced by the caller with
+// launch_advance_counter before this launch) so that the whole update is CUDA-graph capturable.
+int launch_adam_multi(const SgdTensor* d_tensors, int n_tensors, long long max_numel, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, bool decoupled,
+                      const uint64_t* step, float grad_scale, bool zero_grad, cudaStream_t stream);
 int launch_cast_f32_to_bf16(const float* src, void* dst, long long n, cudaStream_t stream);
 int launch_cast_bf16_to_f32(const void* src, float* dst, long long n, cudaStream_t stream);
 

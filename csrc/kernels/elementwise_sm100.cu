@@ -773,6 +773,61 @@ sgd_multi_kernel(const SgdTensor* __restrict__ tensors, float lr, float momentum
   }
 }
 
+// Adam / AdamW over the same descriptors (torch.optim.Adam semantics, experiment/launch.py:152-155
+// accepts any torch.optim name): one launch per stage, moments + master + bf16 shadow + gradient
+// zeroing in one pass = 28 B / parameter.  The bias corrections come from a device-side step
+// counter, so a captured graph replays the right correction every step.
+__global__ void __launch_bounds__(256)
+adam_multi_kernel(const SgdTensor* __restrict__ tensors, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, int decoupled, const uint64_t* __restrict__ step,
+                  float grad_scale, int zero_grad) {
+  const SgdTensor t = tensors[blockIdx.y];
+  const float tstep = static_cast<float>(*step);
+  const float bc1 = 1.f - powf(beta1, tstep);
+  const float bc2_rsqrt = rsqrtf(1.f - powf(beta2, tstep));
+  const float step_size = lr / bc1;
+  const float decay = decoupled ? 1.f - lr * weight_decay : 1.f;
+  const float l2 = decoupled ? 0.f : weight_decay;
+  auto upd = [&](float& p, float gi, float& m, float& v) {
+    p *= decay;
+    const float g = gi * grad_scale + l2 * p;
+    m = beta1 * m + (1.f - beta1) * g;
+    v = beta2 * v + (1.f - beta2) * g * g;
+    p -= step_size * m / (sqrtf(v) * bc2_rsqrt + eps);
+  };
+  const long long n4 = t.numel >> 2;
+  float4* p4 = reinterpret_cast<float4*>(t.p);
+  float4* g4 = reinterpret_cast<float4*>(t.g);
+  float4* m4 = reinterpret_cast<float4*>(t.mom);
+  float4* v4 = reinterpret_cast<float4*>(t.mom2);
+  uint2* b4 = reinterpret_cast<uint2*>(t.p_bf16);
+  for (long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    float4 p = p4[i], m = m4[i], v = v4[i];
+    const float4 g = g4[i];
+    upd(p.x, g.x, m.x, v.x);
+    upd(p.y, g.y, m.y, v.y);
+    upd(p.z, g.z, m.z, v.z);
+    upd(p.w, g.w, m.w, v.w);
+    p4[i] = p;
+    m4[i] = m;
+    v4[i] = v;
+    if (b4 != nullptr) b4[i] = make_uint2(pack_bf16x2(p.x, p.y), pack_bf16x2(p.z, p.w));
+    if (zero_grad && !t.skip_zero) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (blockIdx.x == 0) {
+    for (long long i = (n4 << 2) + threadIdx.x; i < t.numel; i += blockDim.x) {
+      float p = t.p[i], m = t.mom[i], v = t.mom2[i];
+      upd(p, t.g[i], m, v);
+      t.p[i] = p;
+      t.mom[i] = m;
+      t.mom2[i] = v;
+      if (t.p_bf16 != nullptr) reinterpret_cast<__nv_bfloat16*>(t.p_bf16)[i] = __float2bfloat16(p);
+      if (zero_grad) t.g[i] = 0.f;
+    }
+  }
+}
+
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d,
                                      long long n) {
   const long long n4 = n >> 2;
@@ -1037,6 +1092,21 @@ int launch_sgd_multi(const SgdTensor* d_tensors, int n_tensors, long long max_nu
   dim3 grid(static_cast<unsigned>(blocks), n_tensors);
   sgd_multi_kernel<<<grid, 256, 0, stream>>>(d_tensors, lr, momentum, weight_decay, grad_scale,
                                              zero_grad ? 1 : 0);
+  SKY_LAUNCH_CHECK();
+}
+
+int launch_adam_multi(const SgdTensor* d_tensors, int n_tensors, long long max_numel, float lr,
+                      float beta1, float beta2, float eps, float weight_decay, bool decoupled,
+                      const uint64_t* step, float grad_scale, bool zero_grad, cudaStream_t stream) {
+  if (n_tensors <= 0) return 0;
+  if (step == nullptr) return 906;
+  long long blocks = (max_numel / 4 + 255) / 256;
+  if (blocks > 296) blocks = 296;
+  if (blocks < 1) blocks = 1;
+  dim3 grid(static_cast<unsigned>(blocks), n_tensors);
+  adam_multi_kernel<<<grid, 256, 0, stream>>>(d_tensors, lr, beta1, beta2, eps, weight_decay,
+                                              decoupled ? 1 : 0, step, grad_scale,
+                                              zero_grad ? 1 : 0);
   SKY_LAUNCH_CHECK();
 }
 

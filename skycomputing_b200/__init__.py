@@ -44,7 +44,7 @@ from .dataset import *  # noqa: F401,F403
 from .dynamics import *  # noqa: F401,F403
 from .logger import *  # noqa: F401,F403
 from .models import *  # noqa: F401,F403
-from .parallel import (BaseModule, FusedSGD, LocalModule, PipelineEngine, RemoteModule,  # noqa: F401
+from .parallel import (BaseModule, FusedAdam, FusedSGD, LocalModule, PipelineEngine, RemoteModule,  # noqa: F401
                        RpcModel, build_optimizer)
 from .registry import *  # noqa: F401,F403
 from .runner import *  # noqa: F401,F403

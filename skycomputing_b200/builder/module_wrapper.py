@@ -242,15 +242,25 @@ class ModuleWrapper(nn.Module):
                 inputs = step(*inputs)
         return inputs
 
-    def fused_boundary_support(self) -> tuple:
-        """(input side fusable, output side fusable): whole-block cuts on the native path."""
+    def fused_boundary_support(self, shape: Optional[tuple] = None) -> tuple:
+        """(input side fusable, output side fusable): whole-block cuts on the native path.
+
+        ``shape`` = the negotiated ``(micro-batch, seq, hidden)``: when given, the boundary spans
+        must also ``supports()`` it - a span that would fall back to the eager per-layer path
+        (e.g. a non-gelu activation) neither waits on the inbound flags nor writes the peer slot,
+        so it must not be negotiated as fused."""
         if self._plan is None:
             self._plan = self._build_plan()
         from ..models.bert_layers import BertSpan
 
         first, last = self._plan[0], self._plan[-1]
-        return (isinstance(first, BertSpan) and first.head is not None,
-                isinstance(last, BertSpan) and last.tail is not None)
+        in_ok = isinstance(first, BertSpan) and first.head is not None
+        out_ok = isinstance(last, BertSpan) and last.tail is not None
+        if shape is not None and shape[0] and shape[1] and shape[2]:
+            probe = torch.empty(tuple(shape), device="meta")
+            in_ok = in_ok and first.supports(probe)
+            out_ok = out_ok and last.supports(probe)
+        return in_ok, out_ok
 
     def spans(self) -> list:
         from ..models.bert_layers import BertSpan

@@ -67,6 +67,11 @@ class ParameterServer(nn.Module):
             self.module_list[idx].load_state_dict(state_dict)
 
     def get_state_dict(self, idx: int) -> Optional[Dict[str, Tensor]]:
+        if not 0 <= idx < len(self._model_config):
+            raise IndexError("layer index {} out of range (model has {} layers)".format(
+                idx, len(self._model_config)))
         if self._lazy:
-            return self._state.get(idx)
+            # a layer without parameters / buffers never appears in a checkpoint file: its state
+            # dict is empty, not missing (scaelum/dynamics/parameter_server.py:38-39 behaviour)
+            return self._state.get(idx, OrderedDict())
         return self.module_list[idx].state_dict()

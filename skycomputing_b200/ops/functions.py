@@ -118,14 +118,16 @@ class ParamBank:
     def mark_shadow_fresh(self) -> None:
         self._versions = [p._version for p in self.params]
 
-    def sgd_descriptor(self, momentum_buf: Optional[torch.Tensor] = None):
+    def sgd_descriptor(self, momentum_buf: Optional[torch.Tensor] = None,
+                       second_moment: Optional[torch.Tensor] = None):
         self.ensure()
         if self.need_shadow and self._shadow is None:
             self.shadow()
         return (self.flat.data_ptr(), self.flat_grad.data_ptr(),
                 0 if momentum_buf is None else momentum_buf.data_ptr(),
                 self._shadow.data_ptr() if (self.need_shadow and self._shadow is not None) else 0,
-                self.flat.numel(), 1 if self.overwrite_first else 0)
+                self.flat.numel(), 1 if self.overwrite_first else 0,
+                0 if second_moment is None else second_moment.data_ptr())
 
 
 class SpanParams:

@@ -13,9 +13,16 @@ bump the panel flags with ``red.release.sys``.  Consumers (the QKV GEMM's TMA pr
 LayerNorm-backward warps) poll the flags with ``ld.acquire.sys``.  Flags are cumulative and never
 reset: slot *j* is written exactly once per step, so after step *s* a complete panel reads
 ``s * signals_per_panel`` and consumers wait for ``epoch * signals_per_panel`` where ``epoch`` is
-a device-side step counter (CUDA-graph friendly).  No acknowledgement channel is needed: a slot is
-only re-written in step *s+1* after the consumer's own step-*s* traffic in the opposite direction
-proves it was consumed.
+a device-side step counter (CUDA-graph friendly).
+
+Slot re-use: a GRADIENT slot is only re-written in step *s+1* after this rank's own step-*s+1*
+forward traffic, which is stream-ordered behind everything that read the slot.  An ACTIVATION slot
+has one reader that is NOT ordered by opposite-direction traffic: the deferred QKV weight gradient
+(side stream, flushed after the dgrad GEMM has already published the input gradient).  It is
+covered by a one-word ACK per link and step: the consumer bumps the producer's ack word with
+``red.release.sys`` once its weight gradients of the step have joined, and the producer waits for
+``ack >= epoch`` (the word starts at 1) before its first forward of the next step.  The wait is
+free in practice - the consumer of a link finishes its backward before its producer does.
 
 Reference: replaces the CPU-staged TensorPipe hop ``rref.to_here()`` of
 scaelum/builder/module_wrapper.py:148-175 and the distributed-autograd gradient hop of
@@ -60,9 +67,11 @@ class BoundaryRegion:
         # panel flags followed by ONE extra flag that guards the mask slot
         self.flag_bytes = (((self.panels + 1) * 4 + 255) // 256) * 256
         self.stride = self.slot_bytes + self.mask_bytes + self.flag_bytes
-        self.nbytes = n_slots * self.stride
+        # one trailing 256-byte line holds the per-link ack word (see the module docstring)
+        self.nbytes = n_slots * self.stride + 256
         self.ptr, self.handle = nat.ext().ipc_alloc(self.nbytes)
         self.device = device
+        tensor_from_ptr(self.ack_ptr(), (1,), torch.int32, device).fill_(1)
 
     def layout(self) -> dict:
         return dict(n_slots=self.n_slots, rows=self.rows, cols=self.cols, stride=self.stride,
@@ -79,6 +88,9 @@ class BoundaryRegion:
 
     def mask_flag_ptr(self, slot: int, base: Optional[int] = None) -> int:
         return self.flags_ptr(slot, base) + 4 * self.panels
+
+    def ack_ptr(self, base: Optional[int] = None) -> int:
+        return (self.ptr if base is None else base) + self.n_slots * self.stride
 
     def free(self) -> None:
         if self.ptr:
@@ -148,6 +160,21 @@ class FusedChannel:
     def grad_ld(self) -> int:
         return self.peer_layout["cols"]
 
+    # ---- activation-slot acknowledgement (one word per link, lives in the PRODUCER's gradient
+    # region, which the consumer has mapped for its gradient stores anyway) --------------------
+    def ack_consumed(self) -> None:
+        """Consumer side (channel to the previous stage): everything of this step that read the
+        inbound activation slots is stream-ordered before this call."""
+        lay = self.peer_layout
+        nat.ext().signal_flags(self.peer_base + lay["n_slots"] * lay["stride"], 1, 1,
+                               torch.cuda.current_stream().cuda_stream)
+
+    def wait_consumer_ack(self) -> None:
+        """Producer side (channel to the next stage): the consumer has finished every read of the
+        slots it received in the previous step."""
+        nat.ext().wait_flags(self.local.ack_ptr(), 1, self.epoch_ptr, 1, self.error_ptr,
+                             torch.cuda.current_stream().cuda_stream)
+
     def send_mask(self, mask: torch.Tensor, mb: int) -> None:
         """Copy the additive attention mask next to the activation slot of the next stage."""
         m = mask.reshape(-1).contiguous().float()
@@ -189,12 +216,10 @@ class FusedBoundaryManager:
         next_idx = (stage_index + 1) % num_stages
         my_rank = dist.get_rank(group)
         if has_prev:
-            ext.enable_peer_access(self._local_device_of(stage_to_rank[prev_idx]))
             self.prev = FusedChannel(device, self.epoch_ptr, self.error_ptr)
             self.prev.local = BoundaryRegion(micro_batches, rows, cols, mask_elems, device)
             self._regions.append(self.prev.local)
         if has_next:
-            ext.enable_peer_access(self._local_device_of(stage_to_rank[next_idx]))
             self.next = FusedChannel(device, self.epoch_ptr, self.error_ptr)
             self.next.local = BoundaryRegion(micro_batches, rows, cols, 0, device)
             self._regions.append(self.next.local)
@@ -205,7 +230,7 @@ class FusedBoundaryManager:
                 ch.grad_wait_mult = grad_mult
                 ch.rows, ch.cols = rows, cols
         # exchange handles: everybody publishes {to_prev: handle of my act region, to_next: grad}
-        mine: Dict[str, object] = {"rank": my_rank}
+        mine: Dict[str, object] = {"rank": my_rank, "gpu": self._gpu_uuid(device)}
         if has_prev:
             mine["act"] = (self.prev.local.handle, self.prev.local.layout())
         if has_next:
@@ -214,6 +239,12 @@ class FusedBoundaryManager:
         gathered: List[dict] = [None] * world  # type: ignore[list-item]
         dist.all_gather_object(gathered, mine, group=group)
         by_rank = {g["rank"]: g for g in gathered}
+        # a neighbour's GPU is identified by UUID, not by assuming rank == CUDA ordinal: the
+        # ordinal of the same physical GPU differs between processes under CUDA_VISIBLE_DEVICES
+        for idx, present in ((prev_idx, has_prev), (next_idx, has_next)):
+            if present:
+                ext.enable_peer_access(self._local_device_of(by_rank[stage_to_rank[idx]]["gpu"],
+                                                             stage_to_rank[idx]))
         if has_next:   # I write activations into next stage's "act" region
             handle, lay = by_rank[stage_to_rank[next_idx]]["act"]
             self.next.peer_base = ext.ipc_open(handle)
@@ -224,12 +255,34 @@ class FusedBoundaryManager:
             self.prev.peer_base = ext.ipc_open(handle)
             self.prev.peer_layout = lay
             self._opened.append(self.prev.peer_base)
+        torch.cuda.synchronize(device)   # the ack words are initialised before anybody proceeds
         dist.barrier(group=group)
 
     @staticmethod
-    def _local_device_of(rank: int) -> int:
-        # one process per GPU of one node: global rank == CUDA device ordinal
-        return rank % max(torch.cuda.device_count(), 1)
+    def _gpu_uuid(device: torch.device) -> str:
+        return str(torch.cuda.get_device_properties(device).uuid)
+
+    @staticmethod
+    def _local_device_of(uuid: str, rank: int) -> int:
+        """CUDA ordinal, in THIS process, of the GPU with that UUID (the peer rank's device)."""
+        for i in range(torch.cuda.device_count()):
+            if str(torch.cuda.get_device_properties(i).uuid) == uuid:
+                return i
+        raise RuntimeError(
+            f"the GPU of rank {rank} ({uuid}) is not visible to this process: fused stage "
+            "boundaries need every neighbour's GPU in CUDA_VISIBLE_DEVICES (peer access)")
+
+    def begin_step(self) -> None:
+        """Advance the flag epoch; as a producer, wait for last step's consumer acknowledgement."""
+        self.advance_epoch()
+        if self.next is not None:
+            self.next.wait_consumer_ack()
+
+    def end_of_backward(self) -> None:
+        """Call once all reads of this step's inbound activation slots are stream-ordered before
+        the current point (i.e. after the weight-gradient side stream has joined)."""
+        if self.prev is not None:
+            self.prev.ack_consumed()
 
     def advance_epoch(self) -> None:
         nat.ext().advance_epoch(self.epoch_ptr, 1, torch.cuda.current_stream().cuda_stream)

@@ -25,6 +25,7 @@ import torch
 import torch.distributed as dist
 
 from ..builder.module_wrapper import ModuleWrapper
+from .engine_base import EngineBase
 
 
 def one_f_one_b_order(stage: int, num_stages: int, micro_batches: int) -> List[tuple]:
@@ -51,7 +52,7 @@ def sequential_order(stage: int, num_stages: int, micro_batches: int) -> List[tu
     return order
 
 
-class PipelineEngine:
+class PipelineEngine(EngineBase):
     def __init__(self, stage: ModuleWrapper, stage_index: int, num_stages: int,
                  stage_to_rank: Sequence[int], device: torch.device, optimizer,
                  loss_fn: Optional[Callable] = None, micro_batches: int = 1,
@@ -86,33 +87,9 @@ class PipelineEngine:
         self._pending_sends: list = []
         self.stage.engine_managed_backward = True
         self.launches_per_step = 0
-        self._defer_wgrad = False
-        self._wgrad_stream = None
-        self._wgrad_forked = False
-        self._wgrad_keepalive: list = []
-        self._wgrad_tslot: Optional[torch.Tensor] = None
-        import os as _os
-
-        # inline | lazy (queue, flush in front of the next backward) | lazy_stream (same, on a side
-        # stream) | immediate (side stream, forked at the producing kernel) | auto
-        self._wgrad_mode = _os.environ.get("SKY_WGRAD", "auto")
-        self._wgrad_side_stream_enabled = False
-        self._wgrad_immediate = False
-        # device-side timeline (SKY_TRACE=1 or enable_trace()): one %globaltimer stamp in front of
-        # and behind every F / B / W / optimizer phase, written by 1-thread kernels so that the
-        # stamps survive CUDA-graph capture
-        self._trace = _os.environ.get("SKY_TRACE", "0") == "1"
-        self._nvtx = _os.environ.get("SKY_NVTX", "0") == "1"
-        self._trace_buf: Optional[torch.Tensor] = None
-        self._trace_tags: list = []
+        self._init_common()
 
     # ------------------------------------------------------------------ setup
-    def _native_active(self) -> bool:
-        from ..models.bert_layers import get_backend
-        from ..ops import native as nat
-
-        return self.device.type == "cuda" and get_backend() != "torch" and nat.available()
-
     def _setup(self, inputs: Optional[Sequence[torch.Tensor]]) -> None:
         multi = self.P > 1
         shape = [0, 0]
@@ -130,10 +107,10 @@ class PipelineEngine:
         in_ok = out_ok = False
         hidden = 0
         if want_fused:
-            in_ok, out_ok = self.stage.fused_boundary_support()
             spans = self.stage.spans()
             if spans:
                 hidden = self._hidden_size(spans[0])
+            in_ok, out_ok = self.stage.fused_boundary_support((self.mb_batch, self.seq, hidden))
             shape_ok = self.seq == 128 and hidden % 64 == 0 and (self.mb_batch * self.seq) % 128 == 0
             if spans and spans[0].head is not None:
                 shape_ok = shape_ok and spans[0].head.attention.self.attention_head_size == 64
@@ -160,26 +137,17 @@ class PipelineEngine:
                 from .comm import TorchDistComm
 
                 self.comm = TorchDistComm(self.device, group=self.group)
+        # only an optimizer whose step() is pure device work may be captured (a torch.optim class
+        # behind TorchOptimizerAdapter keeps host-side state and refreshes the bf16 shadows through
+        # a host-side version check: replaying it would train on stale weights)
         self.graphable = self._want_graph and self._native_active() and \
-            (self.is_first or self.in_fused) and (self.is_last or self.out_fused)
+            (self.is_first or self.in_fused) and (self.is_last or self.out_fused) and \
+            bool(getattr(self.optimizer, "graph_safe", False))
         if self.graphable:
             # device timers cannot be recorded inside a captured graph
             self.stage._record_forward_time = False
             self.stage._logger = None
-        if self._native_active():
-            from ..ops.functions import set_wgrad_deferral, set_wgrad_stream
-
-            mode = self._wgrad_mode
-            if mode == "auto":
-                mode = "lazy_stream" if multi else "immediate"  # measured best (profiles/bench_history.md)
-            if mode in ("lazy", "lazy_stream") and multi:
-                self._defer_wgrad = True
-                self._wgrad_side_stream_enabled = mode == "lazy_stream"
-                set_wgrad_deferral(True)
-            elif mode in ("immediate", "lazy_stream"):
-                self._wgrad_stream = torch.cuda.Stream(device=self.device)
-                self._wgrad_immediate = True
-                set_wgrad_stream(self._wgrad_stream)
+        self._configure_wgrad(multi)
         self._order = (one_f_one_b_order if self.schedule == "1f1b" else sequential_order)(
             self.s, self.P, self.m)
         self._setup_done = True
@@ -268,89 +236,8 @@ class PipelineEngine:
             return None
         return self._in_grads(args)
 
-    def _flush_wgrads(self) -> None:
-        """Launch the queued weight gradients.  They are independent of the input-gradient chain,
-        so they go to a side stream and run CONCURRENTLY with the next micro-batch's kernels
-        (most of which are single-wave GEMMs that leave SMs idle); the side stream is forked from
-        / joined to the main stream with events, which CUDA-graph capture records as parallel
-        branches."""
-        if not self._defer_wgrad:
-            return
-        from ..ops.functions import flush_wgrads, pending_wgrads
-
-        if pending_wgrads() == 0:
-            return
-        if not self._wgrad_side_stream_enabled:
-            self._mark(("W", -1, "begin"))
-            flush_wgrads()
-            self._mark(("W", -1, "end"))
-            return
-        if self._wgrad_stream is None:
-            self._wgrad_stream = torch.cuda.Stream(device=self.device)
-        main = torch.cuda.current_stream(self.device)
-        self._wgrad_stream.wait_stream(main)
-        slow = float(getattr(self.stage, "_slowdown", 0) or 0)
-        with torch.cuda.stream(self._wgrad_stream):
-            self._mark(("W", -1, "begin"))
-            if slow > 0:
-                # a simulated slow device is slow for its weight gradients too (own time slot: the
-                # stage's forward/backward throttle may be running on the main stream right now)
-                from ..ops import native as nat
-
-                if self._wgrad_tslot is None:
-                    self._wgrad_tslot = torch.zeros(1, dtype=torch.int64, device=self.device)
-                side = self._wgrad_stream.cuda_stream
-                nat.ext().record_time(self._wgrad_tslot.data_ptr(), side)
-            self._wgrad_keepalive.extend(flush_wgrads())
-            if slow > 0:
-                nat.ext().spin_factor(self._wgrad_tslot.data_ptr(), slow, side)
-            self._mark(("W", -1, "end"))
-        self._wgrad_forked = True
-
-    def _join_wgrads(self) -> None:
-        if self._wgrad_immediate:
-            from ..ops.functions import wgrad_keepalive
-
-            torch.cuda.current_stream(self.device).wait_stream(self._wgrad_stream)
-            wgrad_keepalive().clear()
-            return
-        if self._wgrad_forked:
-            torch.cuda.current_stream(self.device).wait_stream(self._wgrad_stream)
-            self._wgrad_forked = False
-        self._wgrad_keepalive.clear()
-
-    # ------------------------------------------------------------------ device timeline
-    def enable_trace(self) -> None:
-        assert self._graph is None, "enable_trace() must precede CUDA-graph capture"
-        self._trace = True
-
-    def _mark(self, tag) -> None:
-        if self._nvtx and self.device.type == "cuda":
-            # NVTX ranges for nsys / ncu --nvtx (host-side: they bracket the LAUNCHES of a phase)
-            if tag[2] == "begin":
-                torch.cuda.nvtx.range_push(f"{tag[0]}{tag[1]}")
-            else:
-                torch.cuda.nvtx.range_pop()
-        if not self._trace or self.device.type != "cuda":
-            return
-        from ..ops import native as nat
-
-        if self._trace_buf is None:
-            self._trace_buf = torch.zeros(8 * (2 * self.m + 4) + 64, dtype=torch.int64, device=self.device)
-        i = len(self._trace_tags)
-        if i >= self._trace_buf.numel():
-            return
-        self._trace_tags.append(tag)
-        nat.ext().record_time(self._trace_buf.data_ptr() + 8 * i,
-                              torch.cuda.current_stream(self.device).cuda_stream)
-
-    def trace(self) -> list:
-        """[(tag, ns)] of the LAST executed step: tags are ('F'|'B'|'W'|'OPT', j, 'begin'|'end')."""
-        if self._trace_buf is None:
-            return []
-        torch.cuda.synchronize(self.device)
-        t = self._trace_buf.cpu().tolist()
-        return [(tag, t[i]) for i, tag in enumerate(self._trace_tags)]
+    def _slowdown_factor(self) -> float:
+        return float(getattr(self.stage, "_slowdown", 0) or 0)
 
     # ------------------------------------------------------------------ comm helpers (unfused)
     @staticmethod
@@ -417,7 +304,7 @@ class PipelineEngine:
         from ..models.bert_layers import advance_rng
 
         if self.fused is not None:
-            self.fused.advance_epoch()
+            self.fused.begin_step()
         if self._advance_rng and self._native_active():
             advance_rng()
         self._loss_acc.zero_()
@@ -462,6 +349,8 @@ class PipelineEngine:
                         self._send_backward(in_grads)
         self._flush_wgrads()
         self._join_wgrads()
+        if self.fused is not None:
+            self.fused.end_of_backward()
         self._mark(("OPT", 0, "begin"))
         self.optimizer.step()
         self._mark(("OPT", 0, "end"))
@@ -475,6 +364,7 @@ class PipelineEngine:
         if not self._setup_done:
             self._setup(inputs)
             self._loss_acc = torch.zeros((), dtype=torch.float32, device=self.device)
+        self._check_batch(inputs, labels)
         if not self.graphable:
             self._step_body(inputs, labels)
             return self._loss_acc if self.is_last else None
@@ -535,12 +425,4 @@ class PipelineEngine:
         if self.fused is not None:
             self.fused.close()
             self.fused = None
-        # the gradient deferral / side stream are process-wide switches of ops.functions: hand them
-        # back so that code running without an engine afterwards gets inline gradients again
-        if self._defer_wgrad or self._wgrad_immediate:
-            from ..ops.functions import set_wgrad_deferral, set_wgrad_stream
-
-            if self._defer_wgrad:
-                set_wgrad_deferral(False)
-            set_wgrad_stream(None)
-            self._defer_wgrad = self._wgrad_immediate = False
+        self._release_wgrad_switches()

@@ -32,6 +32,7 @@ import torch
 import torch.distributed as dist
 
 from .comm import TorchDistComm
+from .engine_base import EngineBase
 
 
 def looped_order(num_chunks: int, micro_batches: int) -> List[tuple]:
@@ -41,7 +42,7 @@ def looped_order(num_chunks: int, micro_batches: int) -> List[tuple]:
     return order
 
 
-class LoopedPipelineEngine:
+class LoopedPipelineEngine(EngineBase):
     def __init__(self, stages: Sequence, virtual_indices: Sequence[int], num_ranks: int,
                  ring: Sequence[int], device: torch.device, optimizer,
                  loss_fn: Optional[Callable] = None, micro_batches: int = 1, group=None,
@@ -81,7 +82,7 @@ class LoopedPipelineEngine:
         self.in_fused = self.out_fused = False
         self.launches_per_step = 0
         self._graph = None
-        self._defer_wgrad = False
+        self._init_common()
         self._setup_done = False
         self.boundary = boundary
         self._want_graph = use_cuda_graph and device.type == "cuda"
@@ -98,12 +99,6 @@ class LoopedPipelineEngine:
             self._comm = TorchDistComm(self.device, group=self.group)
         return self._comm
 
-    def _native_active(self) -> bool:
-        from ..models.bert_layers import get_backend
-        from ..ops import native as nat
-
-        return self.device.type == "cuda" and get_backend() != "torch" and nat.available()
-
     @staticmethod
     def _diff_flags(tensors) -> List[bool]:
         n = len(tensors)
@@ -116,20 +111,16 @@ class LoopedPipelineEngine:
                 t.requires_grad_(True)
         return tuple(tensors)
 
-    def _flush_wgrads(self) -> None:
-        if self._defer_wgrad:
-            from ..ops.functions import flush_wgrads
+    def _slowdown_factor(self) -> float:
+        return max(float(getattr(st, "_slowdown", 0) or 0) for st in self.stages)
 
-            flush_wgrads()
+    def _trace_slots(self) -> int:
+        return 8 * (2 * self.v * self.m + 4) + 64
 
     # ------------------------------------------------------------------ setup (collective)
     def _setup(self, inputs) -> None:
         self._loss_acc = torch.zeros((), dtype=torch.float32, device=self.device)
-        if self._native_active():
-            from ..ops.functions import set_wgrad_deferral
-
-            self._defer_wgrad = True
-            set_wgrad_deferral(True)
+        self._configure_wgrad(True)
         want_fused = self.boundary in ("auto", "fused") and self._native_active()
         shape = [0, 0]
         if self.is_first:
@@ -142,14 +133,14 @@ class LoopedPipelineEngine:
             ok = True
             for c, st in enumerate(self.stages):
                 k = self.vidx[c]
-                in_ok, out_ok = st.fused_boundary_support()
-                ok = ok and (in_ok or k == 0) and (out_ok or k == self.total - 1)
                 spans = st.spans()
                 if spans:
                     sp = spans[0]
                     if sp.head is not None:
                         hidden = sp.head.attention.output.dense.weight.shape[0]
                         ok = ok and sp.head.attention.self.attention_head_size == 64
+                in_ok, out_ok = st.fused_boundary_support((self.mb_batch, self.seq, hidden))
+                ok = ok and (in_ok or k == 0) and (out_ok or k == self.total - 1)
             ok = ok and self.seq == 128 and hidden > 0 and hidden % 64 == 0 and \
                 (self.mb_batch * self.seq) % 128 == 0
         flags = [None] * dist.get_world_size(self.group)
@@ -162,7 +153,7 @@ class LoopedPipelineEngine:
                                               max(f[1] for f in flags), rows, self.device,
                                               group=self.group, ring=True)
             self.in_fused = self.out_fused = True
-            self.graphable = self._want_graph
+            self.graphable = self._want_graph and bool(getattr(self.optimizer, "graph_safe", False))
             if self.graphable:
                 for st in self.stages:
                     st._record_forward_time = False
@@ -186,10 +177,12 @@ class LoopedPipelineEngine:
         transfers at all, the kernels of neighbouring ranks hand panels to each other."""
         from ..models.bert_layers import advance_rng
 
-        self.fused.advance_epoch()
+        self.fused.begin_step()
         if self._advance_rng:
             advance_rng()
         self._loss_acc.zero_()
+        self._trace_tags = []
+        self._mark(("STEP", 0, "begin"))
         chunks_in = [t.chunk(self.m, dim=0) for t in inputs] if self.is_first else None
         label_chunks = labels.chunk(self.m, dim=0) if (self.is_last and labels is not None) else None
         saved = {}
@@ -205,7 +198,9 @@ class LoopedPipelineEngine:
                 args = tuple(t[j] for t in chunks_in) if first_stage else self._fused_inputs(slot)
                 if not last_stage and not first_stage:
                     self.fused.next.send_mask(args[-1], slot)   # the mask travels with the slot
+                self._mark(("F", slot, "begin"))
                 outs = st(*args)
+                self._mark(("F", slot, "end"))
                 if not last_stage and first_stage:
                     self.fused.next.send_mask(outs[-1], slot)   # produced by the embeddings here
                 loss = None
@@ -220,6 +215,7 @@ class LoopedPipelineEngine:
             else:
                 outs, loss = saved.pop((c, j))
                 self._flush_wgrads()
+                self._mark(("B", slot, "begin"))
                 st.begin_backward()
                 if last_stage:
                     if isinstance(loss, tuple):
@@ -229,14 +225,20 @@ class LoopedPipelineEngine:
                 else:
                     torch.autograd.backward([outs[0]], [torch.zeros_like(outs[0])])
                 st.end_backward()
+                self._mark(("B", slot, "end"))
         self._flush_wgrads()
+        self._join_wgrads()
+        self.fused.end_of_backward()
+        self._mark(("OPT", 0, "begin"))
         self.optimizer.step()
+        self._mark(("OPT", 0, "end"))
 
     # ------------------------------------------------------------------ one optimisation step
     def train_step(self, inputs: Optional[Sequence[torch.Tensor]] = None,
                    labels: Optional[torch.Tensor] = None) -> Optional[torch.Tensor]:
         if not self._setup_done:
             self._setup(inputs)
+        self._check_batch(inputs, labels)
         if self.fused is not None:
             return self._train_step_fused(inputs, labels)
         if self._advance_rng and self._native_active():
@@ -294,6 +296,7 @@ class LoopedPipelineEngine:
                     self._pending += self.comm.send(in_grads, self.prev_rank, f"bwd{c}",
                                                     with_meta=False)
         self._flush_wgrads()
+        self._join_wgrads()
         self.optimizer.step()
         self.comm.wait(self._pending)
         self._pending = []
@@ -354,14 +357,7 @@ class LoopedPipelineEngine:
         if self.fused is not None:
             self.fused.close()
             self.fused = None
-        if self._defer_wgrad:
-            from ..ops.functions import set_wgrad_deferral
-
-            set_wgrad_deferral(False)
-            self._defer_wgrad = False
-
-    def trace(self) -> list:
-        return []
+        self._release_wgrad_switches()
 
     @staticmethod
     def barrier(group=None) -> None:

@@ -33,11 +33,12 @@ def _dist():
 class CheckpointHook(Hook):
     def __init__(self, load_checkpoint_from: str = None, save_path: str = None,
                  save_interval: int = None, save_optimizer: bool = True,
-                 resume_training_state: bool = False):
+                 resume_training_state: bool = False, strict_optimizer: bool = False):
         # resume_training_state=True also restores optimizer state and the epoch / iteration
         # counters from the per-rank ``.extra`` shards (same world size required); the default
         # restores weights only, like the reference.
         self._resume_training_state = resume_training_state
+        self._strict_optimizer = strict_optimizer
         self._load_checkpoint_from = load_checkpoint_from
         self._save_interval = save_interval
         self._save_path = save_path
@@ -55,8 +56,13 @@ class CheckpointHook(Hook):
         for module in runner.model.model:
             if not module.is_local:
                 continue
-            b, e = module.layer_range if module.layer_range is not None else (0, len(per_layer))
-            module.load_weights([per_layer[i] for i in range(b, e)])
+            n_layers = (max(per_layer) + 1) if per_layer else 0
+            if runner.parameter_server is not None:
+                n_layers = max(n_layers, len(runner.parameter_server))
+            b, e = module.layer_range if module.layer_range is not None else (0, n_layers)
+            # layers without parameters / buffers (ReLU, Flatten, Dropout-only ...) have no keys in
+            # the file: they load an empty state dict, as in the reference's ParameterServer path
+            module.load_weights([per_layer.get(i, OrderedDict()) for i in range(b, e)])
         if runner.is_rank0:
             runner.parameter_server.load_weights_from_file(self._load_checkpoint_from)
         extra = self._extra_path(self._load_checkpoint_from, runner.rank)
@@ -65,8 +71,15 @@ class CheckpointHook(Hook):
             if self._save_optimizer and st.get("optimizer") is not None:
                 try:
                     runner.optimizer.load_state_dict(st["optimizer"])
-                except Exception:
-                    pass
+                except Exception as exc:  # a resume with fresh optimizer state must not be silent
+                    msg = "CheckpointHook: optimizer state of {} NOT restored ({}: {})".format(
+                        extra, type(exc).__name__, exc)
+                    if self._strict_optimizer:
+                        raise RuntimeError(msg) from exc
+                    import warnings
+
+                    warnings.warn(msg)
+                    runner._log(msg)
             runner.iter = st.get("iter", runner.iter)
             runner.epoch = st.get("epoch", runner.epoch)
 

@@ -73,6 +73,8 @@ class Runner:
         self.parameter_server = parameter_server
         self.optimizer = optimizer
         self._hooks = []
+        self._hook_impl = []
+        self._fixed_batch = None
         self._epoch = 0
         self._iter = 0
         self._inner_iter = 0
@@ -124,7 +126,11 @@ class Runner:
                 stages=model.local_stages, virtual_indices=model.local_stage_indices, num_ranks=P,
                 ring=model.stage_to_rank[:P], device=self.device, optimizer=self.optimizer,
                 loss_fn=self.loss_function, micro_batches=self.micro_batches,
-                boundary=("fused" if os.environ.get("SKY_LOOPED_FUSED", "0") == "1" else "dist"),
+                # fused NVLink ring + whole-step CUDA graph by default on the native path (validated
+                # on 2/4/8 GPUs, profiles/bench_history.md); SKY_LOOPED_FUSED=0 or
+                # boundary="nccl" selects torch.distributed p2p
+                boundary=("auto" if (self._boundary in ("auto", "fused")
+                                     and os.environ.get("SKY_LOOPED_FUSED", "1") != "0") else "dist"),
                 use_cuda_graph=self._use_cuda_graph)
             model.attach_engine(self.engine)
             return
@@ -184,10 +190,13 @@ class Runner:
     def register_hook(self, hook: Hook) -> None:
         assert isinstance(hook, Hook)
         self._hooks.append(hook)
+        self._hook_impl.append(type(hook).overrides())
 
     def _call_hook(self, fn_name: str) -> None:
-        for hook in self._hooks:
-            getattr(hook, fn_name)(self)
+        # hooks that do not implement `fn_name` are skipped without a Python call
+        for hook, impl in zip(self._hooks, self._hook_impl):
+            if fn_name in impl:
+                hook.fire(self, fn_name)
 
     def _log(self, msg: str) -> None:
         if self._logger is not None:
@@ -252,6 +261,8 @@ class Runner:
                 if self._iter >= self._max_iters or self._stop:
                     break
                 self._inner_iter = batch_index
+                if not self._batch_shape_ok(data):
+                    continue
                 self._log("epoch: {}, iter: {}".format(self._epoch, self._iter))
                 self._call_hook("before_train_iter")
                 if cuda:
@@ -274,6 +285,32 @@ class Runner:
             self._epoch += 1
             self._call_hook("after_train_epoch")
         self._call_hook("after_run")
+
+    def _batch_shape_ok(self, data) -> bool:
+        """The engine fixes the micro-batch shape on the first step (static CUDA-graph buffers,
+        peer slots, cached p2p metas).  Every rank iterates the same seeded loader, so all ranks
+        take the same decision here without communicating: a batch that cannot be split into
+        ``micro_batches`` equal chunks is a configuration error, and a later batch of a different
+        size (the short batch a loader without ``drop_last`` ends an epoch with, as the reference's
+        stock data_config does) is skipped with a log line instead of hanging a neighbour stage in
+        a full-size receive."""
+        first = data[0] if isinstance(data, (list, tuple)) else data
+        if not torch.is_tensor(first) or first.dim() == 0:
+            return True
+        nseq = int(first.shape[0])
+        if self._fixed_batch is None:
+            if nseq % max(self.micro_batches, 1) != 0:
+                raise ValueError(
+                    "batch of {} samples cannot be split into {} equal micro-batches".format(
+                        nseq, self.micro_batches))
+            self._fixed_batch = nseq
+            return True
+        if nseq != self._fixed_batch:
+            self._log("skipping a batch of {} samples: the pipeline was set up for batches of {} "
+                      "(use drop_last=True to avoid the short batch at the end of an epoch)".format(
+                          nseq, self._fixed_batch))
+            return False
+        return True
 
     def _check_boundary_health(self, every: int = 50) -> None:
         """Failure detection for the in-kernel cross-GPU flag protocol: every spin-wait has a 4 s

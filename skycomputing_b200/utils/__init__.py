@@ -44,7 +44,10 @@ def load_weights(model: nn.Module, state_dict: List[Dict]) -> None:
 def weights_to_cpu(state_dict):
     out = OrderedDict()
     for key, val in state_dict.items():
-        out[key] = val.detach().float().cpu()
+        # only floating-point entries are widened to fp32; integer buffers (e.g. BatchNorm's
+        # num_batches_tracked) keep their dtype so the file stays format-identical
+        val = val.detach()
+        out[key] = (val.float() if val.is_floating_point() else val).cpu()
     return out
 
 

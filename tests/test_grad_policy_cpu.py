@@ -138,8 +138,11 @@ def test_looped_fused_step_body_order_and_slots(monkeypatch):
     class Fused:
         prev, next = Chan("prev"), Chan("next")
 
-        def advance_epoch(self):
+        def begin_step(self):          # advance the epoch + wait for the consumer's ack
             log.append(("epoch",))
+
+        def end_of_backward(self):     # acknowledge the inbound activation slots
+            log.append(("ack",))
 
     class Opt:
         def step(self):
@@ -169,5 +172,7 @@ def test_looped_fused_step_body_order_and_slots(monkeypatch):
         assert all(e[1] == "next" for e in masks)
         assert sorted(e[2] for e in masks) == ([0, 1, 2, 3] if pos == 0 else [0, 1])
         assert log[0] == ("epoch",) and log[-1] == ("opt",) and log.count(("opt",)) == 1
+        # the slot acknowledgement goes out after the last backward and before the optimizer
+        assert log[-2] == ("ack",) and log.count(("ack",)) == 1
         if pos == 1:
             assert float(eng._loss_acc) > 0
