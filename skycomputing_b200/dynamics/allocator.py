@@ -28,19 +28,33 @@ _BLOCK_SEQ = ("BertLayer_Head", "BertLayer_Body", "BertLayer_Tail")
 
 
 def group_units(model_cfg: Sequence[dict], granularity: str) -> List[tuple]:
-    """[(begin, end)] index ranges of the allocatable units of the layer list."""
+    """[(begin, end)] index ranges of the allocatable units of the layer list.
+
+    ``"layer"``: every list entry is a unit (the reference's granularity).  ``"block"``: a
+    ``Head, Body, Tail`` triple is one unit, and the entries in front of the first / behind the
+    last transformer block (embeddings; pooler, classifier) belong to that block's unit - every
+    cut then sits between two whole blocks, which is where the fused NVLink boundary exists."""
     n = len(model_cfg)
     if granularity == "layer":
         return [(i, i + 1) for i in range(n)]
-    units, i = [], 0
+    units, is_block, i = [], [], 0
     while i < n:
         names = [c.get("layer_type") for c in model_cfg[i:i + 3]]
         if tuple(names) == _BLOCK_SEQ:
             units.append((i, i + 3))
+            is_block.append(True)
             i += 3
         else:
             units.append((i, i + 1))
+            is_block.append(False)
             i += 1
+    if any(is_block):
+        first, last = is_block.index(True), len(is_block) - 1 - is_block[::-1].index(True)
+        head = (units[0][0], units[first][1])
+        tail = (units[last][0], units[-1][1])
+        if first == last:
+            return [(head[0], tail[1])]
+        units = [head] + units[first + 1:last] + [tail]
     return units
 
 

@@ -487,12 +487,17 @@ def native_param_banks(module: nn.Module):
     optimizer and the forward pass share the same flat fp32 / bf16 buffers.
     """
     banks = []
-    spans = getattr(module, "spans", None)
     covered = set()
-    if callable(spans):
-        for span in spans():
-            banks.extend(span.params.banks)
-            covered.update(id(l) for l in span.layers)
+    # every stage runtime (ModuleWrapper) below `module` - `module` itself, or the chunks of a
+    # looped pipeline held in a ModuleList - contributes the banks of ITS fused spans: building
+    # lone per-layer spans for them instead would give the optimizer different flat buffers than
+    # the ones the forward pass reads
+    for m in module.modules():
+        spans = getattr(m, "spans", None)
+        if callable(spans):
+            for span in spans():
+                banks.extend(span.params.banks)
+                covered.update(id(l) for l in span.layers)
     for m in module.modules():
         if id(m) in covered:
             continue

@@ -193,6 +193,9 @@ class BertSpanFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, sp: SpanParams, training: bool, in_ch, out_ch, mb: int, n_in: int, *tensors):
         inputs = tensors[:n_in]
+        # slot index on the inbound link / on the outbound link: the same number in a plain
+        # pipeline (micro-batch j), different ones on the wrap-around link of a looped pipeline
+        mb_in, mb_out = mb if isinstance(mb, tuple) else (mb, mb)
         rng = sp.rng
         p_attn = sp.p_attn if training else 0.0
         p_hid = sp.p_hidden if training else 0.0
@@ -204,7 +207,7 @@ class BertSpanFn(torch.autograd.Function):
             B, S, H = x3.shape
             x = _flat2d(x3)
             mask2 = None if mask is None else mask.reshape(B, S)
-            wait = _ch_kwargs_wait(in_ch, mb) if in_ch is not None else {}
+            wait = _ch_kwargs_wait(in_ch, mb_in) if in_ch is not None else {}
             qkv = nat.gemm(x, sp.wqkv.shadow(), bias=sp.bqkv.master(), **wait)
             ctxt, lse = nat.attention_fwd(qkv, mask2, B, S, sp.heads, dropout_p=p_attn, rng=rng,
                                           rng_stream=sp.rng_base + 1)
@@ -212,7 +215,7 @@ class BertSpanFn(torch.autograd.Function):
                           dropout_p=p_hid, rng=rng, rng_stream=sp.rng_base + 2)
             ln_out = {}
             if out_ch is not None and not sp.has_body:
-                ln_out = dict(y_ptr=out_ch.peer_act_ptr(mb), signal_flags=out_ch.peer_act_flags_ptr(mb))
+                ln_out = dict(y_ptr=out_ch.peer_act_ptr(mb_out), signal_flags=out_ch.peer_act_flags_ptr(mb_out))
             y1, mean1, rstd1 = _ln_fwd(z1, sp.g1.master(), sp.b1n.master(), sp.eps, **ln_out)
             saved.update(x=x, mask2=mask2, qkv=qkv, ctxt=ctxt, lse=lse, z1=z1, mean1=mean1,
                          rstd1=rstd1)
@@ -230,7 +233,7 @@ class BertSpanFn(torch.autograd.Function):
                 a = _flat2d(a3)
             shape3 = (B, S, H)
         if sp.has_body:
-            wait = _ch_kwargs_wait(in_ch, mb) if (in_ch is not None and not sp.has_head) else {}
+            wait = _ch_kwargs_wait(in_ch, mb_in) if (in_ch is not None and not sp.has_head) else {}
             I = sp.w1.master().shape[0]
             h1 = torch.empty((a.shape[0], I), dtype=torch.bfloat16, device=a.device)
             inter = nat.gemm(a, sp.w1.shadow(), bias=sp.b1.master(), act=nat.ACT_GELU, out2=h1, **wait)
@@ -238,12 +241,12 @@ class BertSpanFn(torch.autograd.Function):
         elif sp.has_tail:
             inter = _flat2d(inputs[0])
         if sp.has_tail:
-            wait = _ch_kwargs_wait(in_ch, mb) if (in_ch is not None and not sp.has_body) else {}
+            wait = _ch_kwargs_wait(in_ch, mb_in) if (in_ch is not None and not sp.has_body) else {}
             z2 = nat.gemm(inter, sp.w2.shadow(), bias=sp.b2.master(), aux=a, add_aux=True,
                           dropout_p=p_hid, rng=rng, rng_stream=sp.rng_base + 3, **wait)
             ln_out = {}
             if out_ch is not None:
-                ln_out = dict(y_ptr=out_ch.peer_act_ptr(mb), signal_flags=out_ch.peer_act_flags_ptr(mb))
+                ln_out = dict(y_ptr=out_ch.peer_act_ptr(mb_out), signal_flags=out_ch.peer_act_flags_ptr(mb_out))
             y2, mean2, rstd2 = _ln_fwd(z2, sp.g2.master(), sp.b2n.master(), sp.eps, **ln_out)
             saved.update(z2=z2, mean2=mean2, rstd2=rstd2)
         if sp.has_body or sp.has_tail:
@@ -267,7 +270,8 @@ class BertSpanFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *grads):
         sp, sv = ctx.sp, ctx.saved
-        in_ch, out_ch, mb = ctx.in_ch, ctx.out_ch, ctx.mb
+        in_ch, out_ch = ctx.in_ch, ctx.out_ch
+        mb_in, mb_out = ctx.mb if isinstance(ctx.mb, tuple) else (ctx.mb, ctx.mb)
         rng = sp.rng
         p_attn = sp.p_attn if ctx.training else 0.0
         p_hid = sp.p_hidden if ctx.training else 0.0
@@ -279,8 +283,8 @@ class BertSpanFn(torch.autograd.Function):
         if sp.has_tail:
             wait = {}
             if out_ch is not None:
-                dy2 = out_ch.grad_view(mb, M, H)
-                wait = dict(wait_flags=out_ch.grad_flags_ptr(mb), wait_epoch=out_ch.epoch_ptr,
+                dy2 = out_ch.grad_view(mb_out, M, H)
+                wait = dict(wait_flags=out_ch.grad_flags_ptr(mb_out), wait_epoch=out_ch.epoch_ptr,
                             wait_mult=out_ch.grad_wait_mult, error_flag=out_ch.error_ptr)
             else:
                 dy2 = _flat2d(grads[0]).contiguous()
@@ -293,7 +297,7 @@ class BertSpanFn(torch.autograd.Function):
             if sp.has_body:
                 d_h1 = nat.gemm(g2, sp.w2.shadow(), b_mn=True, aux=sv["h1"], act=nat.ACT_DGELU_MUL_AUX)
             else:
-                send = _grad_send_kwargs(in_ch, mb, which=0)
+                send = _grad_send_kwargs(in_ch, mb_in, which=0)
                 d_inter = nat.gemm(g2, sp.w2.shadow(), b_mn=True, **send)
             d_a_extra = dz2
         elif sp.has_body:
@@ -307,7 +311,7 @@ class BertSpanFn(torch.autograd.Function):
                 d_a_extra = _flat2d(grads[1]).contiguous()
         if sp.has_body:
             _wgrad(d_h1, sv["a"], sp.w1, sp.b1)
-            send = _grad_send_kwargs(in_ch, mb, which=0) if not sp.has_head else {}
+            send = _grad_send_kwargs(in_ch, mb_in, which=0) if not sp.has_head else {}
             d_a = nat.gemm(d_h1, sp.w1.shadow(), b_mn=True, aux=d_a_extra,
                            add_aux=d_a_extra is not None, **send)
         elif sp.has_tail:
@@ -318,8 +322,8 @@ class BertSpanFn(torch.autograd.Function):
             wait = {}
             if not sp.has_body:
                 if out_ch is not None:
-                    dy1 = out_ch.grad_view(mb, M, H)
-                    wait = dict(wait_flags=out_ch.grad_flags_ptr(mb), wait_epoch=out_ch.epoch_ptr,
+                    dy1 = out_ch.grad_view(mb_out, M, H)
+                    wait = dict(wait_flags=out_ch.grad_flags_ptr(mb_out), wait_epoch=out_ch.epoch_ptr,
                                 wait_mult=out_ch.grad_wait_mult, error_flag=out_ch.error_ptr)
                 else:
                     dy1 = _flat2d(grads[0]).contiguous()
@@ -335,7 +339,7 @@ class BertSpanFn(torch.autograd.Function):
             dqkv = nat.attention_bwd(sv["qkv"], sv["mask2"], sv["ctxt"], sv["lse"], dctx, B, S,
                                      sp.heads, dropout_p=p_attn, rng=rng, rng_stream=sp.rng_base + 1)
             _wgrad(dqkv, sv["x"], sp.wqkv, sp.bqkv)
-            send = _grad_send_kwargs(in_ch, mb, which=0)
+            send = _grad_send_kwargs(in_ch, mb_in, which=0)
             dx = nat.gemm(dqkv, sp.wqkv.shadow(), b_mn=True, aux=dz1, add_aux=True, **send)
             g_in[0] = None if dx is None else dx.view(B, S, H)
         elif sp.has_body:

@@ -6,6 +6,13 @@ every boundary that cannot be fused into a GEMM / LayerNorm epilogue (and as the
 fused path is measured against).  Opposite-direction transfers of the 1F1B steady state are
 issued as ONE ``batch_isend_irecv`` group so NCCL cannot dead-lock on crossed sends.
 
+``directional=True`` (looped pipelines on NCCL; collective constructor): messages travel on two
+extra communicators, one per direction (sender rank < receiver rank, and the reverse).  NCCL
+executes the p2p operations of one communicator in posting order and a send larger than its
+staging buffer only completes against a posted receive, so on a ring of TWO ranks - where the next
+and the previous neighbour are the same peer - two ranks that both have a send at the head of the
+same communicator dead-lock.  A communicator that carries one direction only cannot cross.
+
 Tensor metadata (count / dtype / shape) is exchanged once per (peer, direction) and cached.
 """
 from __future__ import annotations
@@ -49,12 +56,22 @@ def _decode_meta(meta: torch.Tensor) -> List[Optional[Tuple[torch.dtype, tuple]]
 
 
 class TorchDistComm:
-    def __init__(self, device: torch.device, group=None):
+    def __init__(self, device: torch.device, group=None, directional: bool = False):
         self.device = device
         self.group = group
         self.backend = dist.get_backend(group)
         self._meta_sent: Dict[tuple, bool] = {}
         self._meta_recv: Dict[tuple, list] = {}
+        self._rank = dist.get_rank(group)
+        self._up = self._down = None
+        if directional and self.backend == "nccl" and group is None:
+            self._up = dist.new_group(backend="nccl")      # sender rank < receiver rank
+            self._down = dist.new_group(backend="nccl")    # sender rank > receiver rank
+
+    def _grp(self, sender: int, receiver: int):
+        if self._up is None:
+            return self.group
+        return self._up if sender < receiver else self._down
 
     # -- metadata ---------------------------------------------------------------------------
     def _meta_device(self) -> torch.device:
@@ -63,13 +80,14 @@ class TorchDistComm:
     def _send_meta(self, tensors, dst: int, key: tuple) -> None:
         if key in self._meta_sent:
             return
-        dist.send(_encode_meta(tensors).to(self._meta_device()), dst, group=self.group)
+        dist.send(_encode_meta(tensors).to(self._meta_device()), dst,
+                  group=self._grp(self._rank, dst))
         self._meta_sent[key] = True
 
     def _recv_meta(self, src: int, key: tuple) -> list:
         if key not in self._meta_recv:
             buf = torch.empty(64, dtype=torch.int64, device=self._meta_device())
-            dist.recv(buf, src, group=self.group)
+            dist.recv(buf, src, group=self._grp(src, self._rank))
             self._meta_recv[key] = _decode_meta(buf.cpu())
         return self._meta_recv[key]
 
@@ -81,7 +99,7 @@ class TorchDistComm:
         reqs = []
         for t in tensors:
             if t is not None:
-                reqs.append(dist.isend(t.contiguous(), dst, group=self.group))
+                reqs.append(dist.isend(t.contiguous(), dst, group=self._grp(self._rank, dst)))
         return reqs
 
     def recv(self, src: int, direction: str, metas: Optional[list] = None) -> Tuple[list, list]:
@@ -96,7 +114,7 @@ class TorchDistComm:
                 continue
             dtype, shape = m
             buf = torch.empty(shape, dtype=dtype, device=self.device)
-            reqs.append(dist.irecv(buf, src, group=self.group))
+            reqs.append(dist.irecv(buf, src, group=self._grp(src, self._rank)))
             outs.append(buf)
         return outs, reqs
 

@@ -96,7 +96,7 @@ class LoopedPipelineEngine(EngineBase):
     @property
     def comm(self) -> TorchDistComm:
         if self._comm is None:
-            self._comm = TorchDistComm(self.device, group=self.group)
+            self._comm = TorchDistComm(self.device, group=self.group)   # eval-only use
         return self._comm
 
     @staticmethod
@@ -158,6 +158,9 @@ class LoopedPipelineEngine(EngineBase):
                 for st in self.stages:
                     st._record_forward_time = False
                     st._logger = None
+        if self.fused is None:
+            # collective: one communicator per direction so crossed sends cannot dead-lock NCCL
+            self._comm = TorchDistComm(self.device, group=self.group, directional=True)
         self._setup_done = True
 
     def _fused_inputs(self, slot: int):
@@ -189,20 +192,24 @@ class LoopedPipelineEngine(EngineBase):
         for kind, c, j in self._order:
             k = self.vidx[c]
             st = self.stages[c]
+            # a link's slots are numbered by the CONSUMER's chunk: inbound = this chunk, outbound =
+            # the chunk of virtual stage k + 1 (the same number except on the wrap-around link
+            # from the last ring position to the first, where it is c + 1)
             slot = c * self.m + j
+            out_slot = ((k + 1) // self.P) * self.m + j
             first_stage, last_stage = k == 0, k == self.total - 1
-            st.microbatch = slot
+            st.microbatch = (slot, out_slot)
             st.in_channel = None if first_stage else self.fused.prev
             st.out_channel = None if last_stage else self.fused.next
             if kind == "F":
                 args = tuple(t[j] for t in chunks_in) if first_stage else self._fused_inputs(slot)
                 if not last_stage and not first_stage:
-                    self.fused.next.send_mask(args[-1], slot)   # the mask travels with the slot
+                    self.fused.next.send_mask(args[-1], out_slot)   # the mask travels with the slot
                 self._mark(("F", slot, "begin"))
                 outs = st(*args)
                 self._mark(("F", slot, "end"))
                 if not last_stage and first_stage:
-                    self.fused.next.send_mask(outs[-1], slot)   # produced by the embeddings here
+                    self.fused.next.send_mask(outs[-1], out_slot)   # produced by the embeddings here
                 loss = None
                 if last_stage:
                     if hasattr(self.loss_fn, "fused"):

@@ -104,7 +104,7 @@ def test_fused_sgd_marks_only_wgrad_targets(monkeypatch):
 
 def test_looped_fused_step_body_order_and_slots(monkeypatch):
     """The (GPU-only) fused step body of the looped engine, driven with fakes on CPU: breadth-first
-    order, slot = chunk * m + micro-batch, masks relayed once per slot, first / last virtual stage
+    order, slot = consumer chunk * m + micro-batch, masks relayed once per slot, first / last virtual stage
     special cases, one optimizer step."""
     from skycomputing_b200.parallel.pipeline_looped import LoopedPipelineEngine
 
@@ -162,15 +162,19 @@ def test_looped_fused_step_body_order_and_slots(monkeypatch):
                             lambda slot: (torch.ones(2, 3, requires_grad=True), torch.zeros(2)))
         data = [torch.ones(4, 3, requires_grad=True), torch.zeros(4)]
         eng._step_body_fused(data if pos == 0 else None, torch.zeros(4) if pos == 1 else None)
+        # (inbound slot, outbound slot): a link's slots are numbered by the CONSUMER's chunk, so
+        # the wrap-around link (ring position P-1 -> 0) writes into the slots of chunk c + 1
+        wrap = m if pos == P - 1 else 0
         fwd = [e for e in log if e[0] == "F"]
-        assert [(e[1], e[2]) for e in fwd] == [("c0", 0), ("c0", 1), ("c1", 2), ("c1", 3)]
+        assert [(e[1], e[2]) for e in fwd] == [("c0", (0, 0 + wrap)), ("c0", (1, 1 + wrap)),
+                                               ("c1", (2, 2 + wrap)), ("c1", (3, 3 + wrap))]
         bwd = [e for e in log if e[0] == "B"]
-        assert [(e[1], e[2]) for e in bwd] == [("c1", 2), ("c1", 3), ("c0", 0), ("c0", 1)]
+        assert [(e[1], e[2][0]) for e in bwd] == [("c1", 2), ("c1", 3), ("c0", 0), ("c0", 1)]
         # virtual stage 0 has no inbound channel, the last one no outbound channel
         assert fwd[0][3] == (pos != 0) and fwd[-1][4] == (pos != 1)
         masks = [e for e in log if e[0] == "mask"]
         assert all(e[1] == "next" for e in masks)
-        assert sorted(e[2] for e in masks) == ([0, 1, 2, 3] if pos == 0 else [0, 1])
+        assert sorted(e[2] for e in masks) == ([0, 1, 2, 3] if pos == 0 else [2, 3])
         assert log[0] == ("epoch",) and log[-1] == ("opt",) and log.count(("opt",)) == 1
         # the slot acknowledgement goes out after the last backward and before the optimizer
         assert log[-2] == ("ack",) and log.count(("ack",)) == 1

@@ -241,7 +241,7 @@ class _FakeModelBench:
 
 
 def _train_with_reallocation(rank, world, use_hook, steps, tmp):
-    cfg = _model_cfg(layers=3)
+    cfg = _model_cfg(layers=4)
     wm = sky.WorkerManager(first_rank=0)
     wm.load_worker_pool_from_config([
         dict(name=f"w{i}", server_config={}, device=i,
@@ -294,8 +294,8 @@ def test_reallocate_hook_migrates_layers_without_changing_the_training_result(tm
     tmp = str(tmp_path)
     plain = run_distributed(_train_with_reallocation, 2, False, 5, tmp)
     moved = run_distributed(_train_with_reallocation, 2, True, 5, tmp)
-    # even split of emb + 3 blocks + pooler + classifier at block granularity, then the 3x slower
-    # device 1 sheds blocks to device 0
+    # even split of the 4 block units (emb rides with the first, pooler + classifier with the last
+    # block), then the 3x slower device 1 sheds a block to device 0
     assert plain[0]["range"] != moved[0]["range"]
     assert moved[0]["migrations"] == 1 and moved[1]["migrations"] == 1   # iter 2 moves, iter 4 keeps
     n0 = moved[0]["range"][1] - moved[0]["range"][0]
@@ -311,7 +311,7 @@ def test_reallocate_hook_migrates_layers_without_changing_the_training_result(tm
         sp.update(r["sums"])
     for r in moved:
         sm.update(r["sums"])
-    assert sorted(sp) == sorted(sm) == list(range(12))
+    assert sorted(sp) == sorted(sm) == list(range(15))
     for k in sp:
         assert sm[k] == pytest.approx(sp[k], rel=1e-6), k
 
@@ -319,8 +319,9 @@ def test_reallocate_hook_migrates_layers_without_changing_the_training_result(tm
 # ---------------------------------------------------------------------------------------------
 # Looped (virtual-stage) pipeline: v chunks per rank, ring of ranks
 # ---------------------------------------------------------------------------------------------
-def _train_looped(rank, world, virtual_stages, micro_batches, steps, tmp, alloc, save_to=None):
-    cfg = _model_cfg(layers=4)
+def _train_looped(rank, world, virtual_stages, micro_batches, steps, tmp, alloc, save_to=None,
+                  layers=6):
+    cfg = _model_cfg(layers=layers)
     wm = sky.WorkerManager(first_rank=0)
     wm.load_worker_pool_from_config([
         dict(name=f"w{i}", server_config={}, device=i,
@@ -378,7 +379,7 @@ def test_looped_pipeline_equals_plain_pipeline(tmp_path):
     loop2 = run_distributed(_train_looped, 2, 2, 2, 4, tmp, "even")
     loop3 = run_distributed(_train_looped, 3, 2, 4, 4, tmp, "even")
     assert plain[0]["schedule"] != "looped" and loop2[0]["schedule"] == "looped"
-    assert loop2[0]["chunks"] == [[(0, 4), (10, 14)], [(4, 10), (14, 15)]]
+    assert loop2[0]["chunks"] == [[(0, 7), (13, 16)], [(7, 13), (16, 21)]]
     lp = [r["losses"] for r in plain if r["losses"]][0]
     l2 = [r["losses"] for r in loop2 if r["losses"]][0]
     l3 = [r["losses"] for r in loop3 if r["losses"]][0]
@@ -390,7 +391,7 @@ def test_looped_pipeline_equals_plain_pipeline(tmp_path):
         sp.update(r["sums"])
     for r in loop2:
         s2.update(r["sums"])
-    assert sorted(sp) == sorted(s2) == list(range(15))
+    assert sorted(sp) == sorted(s2) == list(range(21))
     for k in sp:
         assert s2[k] == pytest.approx(sp[k], rel=1e-6), k
 
@@ -401,7 +402,7 @@ def test_looped_allocation_respects_device_speeds(tmp_path):
     chunks = out[0]["chunks"]
     n0 = sum(e - b for b, e in chunks[0])
     n1 = sum(e - b for b, e in chunks[1])
-    assert n0 > n1 and n0 + n1 == 15
+    assert n0 > n1 and n0 + n1 == 21
     assert [r["losses"] for r in out if r["losses"]][0][-1] > 0
 
 
@@ -418,7 +419,7 @@ def test_launcher_looped_pipeline_from_config(tmp_path):
     assert out.returncode == 0, out.stdout + out.stderr
     d = os.path.join(str(tmp_path), "logs", "3nodes_4layers", "even")
     log = open(os.path.join(d, "allocation.log")).read()
-    assert "runs layer spans [(0, 4), (10, 14)]" in log and log.count("step time") == 2
+    assert "runs layer spans [(0, 4), (7, 10)]" in log and log.count("step time") == 2
 
 
 def test_checkpoint_of_a_looped_pipeline_equals_plain_checkpoint(tmp_path):
