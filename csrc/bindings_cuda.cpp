@@ -43,9 +43,15 @@ void gemm(uintptr_t A, uintptr_t B, int M, int N, int K, int lda, int ldb, bool 
           uintptr_t bias, uintptr_t aux, int ldaux, int act, bool add_aux, float dropout_p,
           uintptr_t rng_state, uint32_t rng_stream, uintptr_t signal_flags, uintptr_t wait_flags,
           uintptr_t wait_epoch, uint32_t wait_mult, uintptr_t error_flag, int block_n, int pair, int stream_k, int max_ctas,
-          int debug,
+          int debug, uintptr_t ln_gamma, uintptr_t ln_beta, uintptr_t ln_mean, uintptr_t ln_rstd,
+          float ln_eps,
           uintptr_t stream) {
   GemmArgs a;
+  a.ln_gamma = P<const float>(ln_gamma);
+  a.ln_beta = P<const float>(ln_beta);
+  a.ln_mean = P<float>(ln_mean);
+  a.ln_rstd = P<float>(ln_rstd);
+  a.ln_eps = ln_eps;
   a.A = P<void>(A);
   a.B = P<void>(B);
   a.M = M;
@@ -371,7 +377,13 @@ PYBIND11_MODULE(_cuda, m) {
         py::arg("dropout_p") = 0.f, py::arg("rng_state") = 0, py::arg("rng_stream") = 0,
         py::arg("signal_flags") = 0, py::arg("wait_flags") = 0, py::arg("wait_epoch") = 0,
         py::arg("wait_mult") = 0, py::arg("error_flag") = 0, py::arg("block_n") = 0, py::arg("pair") = -1, py::arg("stream_k") = -1,
-        py::arg("max_ctas") = 0, py::arg("debug") = 0, py::arg("stream") = 0);
+        py::arg("max_ctas") = 0, py::arg("debug") = 0, py::arg("ln_gamma") = 0,
+        py::arg("ln_beta") = 0, py::arg("ln_mean") = 0, py::arg("ln_rstd") = 0,
+        py::arg("ln_eps") = 1e-12f, py::arg("stream") = 0);
+  m.def("gemm_ln_block_n", &sky::gemm_ln_block_n, py::arg("M"), py::arg("N"),
+        py::arg("force") = false);
+  m.def("gemm_ln_tiles_per_panel", &sky::gemm_ln_tiles_per_panel, py::arg("M"), py::arg("N"),
+        py::arg("force") = false);
   m.def("gemm_pick_block_n", &sky::gemm_pick_block_n);
   m.def("gemm_tiles_per_panel", &sky::gemm_tiles_per_panel);
   m.def("layernorm_fwd", &layernorm_fwd, py::arg("z"), py::arg("y"), py::arg("mean"),

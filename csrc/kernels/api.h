@@ -46,6 +46,15 @@ struct GemmArgs {
   const uint32_t* wait_epoch = nullptr;
   uint32_t wait_mult = 0;
   int* error_flag = nullptr;  // set to non-zero on flag-wait timeout
+  // LayerNorm epilogue (ln_gamma != nullptr): out = LN(dropout(A B^T + bias) + aux) * gamma + beta,
+  // out2 = the pre-LN sum (bf16, saved for backward), ln_mean / ln_rstd = row statistics.  The
+  // N / BLOCK_N CTAs of a 128-row panel form a thread-block cluster (row statistics through
+  // DSMEM); `out` may be peer memory, signal_flags[panel] then receives N / BLOCK_N signals.
+  const float* ln_gamma = nullptr;
+  const float* ln_beta = nullptr;
+  float* ln_mean = nullptr;
+  float* ln_rstd = nullptr;
+  float ln_eps = 1e-12f;
   int block_n = 0;            // 0 = auto (128 or 256)
   int stream_k = -1;          // stream-K schedule: -1 auto, 0 off, 1 on
   int pair = -1;              // -1 auto, 0 single CTAs, 1 cta_group::2 pairs, 2 = 4-CTA clusters: two pairs + A multicast
@@ -55,6 +64,11 @@ struct GemmArgs {
 
 // Returns 0 on success, a cudaError_t / CUresult-like code otherwise.
 int launch_gemm(const GemmArgs& args, cudaStream_t stream);
+int launch_gemm_ln(const GemmArgs& args, cudaStream_t stream);
+// tile width the fused LN epilogue would use (0 = use GEMM + standalone LayerNorm instead; with
+// `force` only when the kernel cannot run the shape at all) / signals per 128-row panel
+int gemm_ln_block_n(int M, int N, bool force = false);
+int gemm_ln_tiles_per_panel(int M, int N, bool force = false);
 int gemm_tiles_per_panel(int N, int block_n);  // number of signals per 128-row panel
 int gemm_pick_block_n(int M, int N);
 bool gemm_pick_pair(int M, int N, int K);

@@ -700,6 +700,393 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
   }
 }
 
+
+// ------------------------------------------------------------------------------------------
+// GEMM + bias + dropout + residual + LayerNorm in ONE kernel:
+//
+//     y = LayerNorm( dropout(A W^T + bias) + residual ) * gamma + beta        z = the pre-LN sum
+//
+// A LayerNorm row spans all N columns, a CTA's accumulator only BLOCK_N of them, so the N / BLOCK_N
+// CTAs that own the column tiles of one 128-row panel form a THREAD-BLOCK CLUSTER (2..8 CTAs) and
+// exchange per-row partial sums through distributed shared memory:
+//
+//   pass 1  TMEM -> registers: + bias, dropout, + residual; store z (bf16, saved for backward);
+//           accumulate row sum / sum of squares; write the fp32 values BACK into the accumulator's
+//           own TMEM columns (tcgen05.st) - 128 x BLOCK_N fp32 do not fit in registers
+//   DSMEM   every row-owner thread stores its (sum, sumsq) into ALL CTAs of the cluster
+//           (st.shared::cluster) and arrives on their mbarriers (release.cluster)
+//   pass 2  TMEM -> registers again: normalise with the cluster-wide statistics, gamma / beta,
+//           store y - straight into the NEXT PIPELINE STAGE's HBM when y is a peer pointer, then
+//           one red.release.sys per CTA on the panel flag.
+//
+// This is the forward stage boundary of the north star: the last GEMM of stage i stores its
+// output tiles into stage i+1's HBM from inside the tcgen05 kernel; no separate LayerNorm launch.
+// Reference ops replaced: scaelum/model/bert_layers.py:285-289 (BertSelfOutput) and :323-327
+// (BertOutput); hop replaced: scaelum/builder/module_wrapper.py:148-175.
+// ------------------------------------------------------------------------------------------
+struct GemmLnDev {
+  int M, N, K;
+  void* y;
+  void* z;
+  long long ldy, ldz, ldaux;
+  const float* bias;
+  const __nv_bfloat16* aux;
+  const float* gamma;
+  const float* beta;
+  float* mean;
+  float* rstd;
+  float eps;
+  float dropout_p;
+  const uint64_t* rng_state;
+  uint32_t rng_stream;
+  uint32_t* signal_flags;
+  const uint32_t* wait_flags;
+  const uint32_t* wait_epoch;
+  uint32_t wait_mult;
+  int* error_flag;
+};
+
+constexpr int kLnMaxCluster = 8;
+
+template <int BLOCK_N>
+struct LnCfg {
+  using C = Cfg<BLOCK_N, false>;
+  static constexpr int kStages = C::kStages;
+  static constexpr int kVecBytes = 3 * BLOCK_N * 4;                 // bias, gamma, beta
+  static constexpr int kStatsBytes = kLnMaxCluster * BLOCK_M * 8;   // float2 per (cta, row)
+  static constexpr int kOffBars = kStages * C::kStageBytes;
+  static constexpr int kOffVec = kOffBars + 256;
+  static constexpr int kOffOut = kOffVec + kVecBytes;
+  static constexpr int kOffStats = kOffOut + C::kOutStageBytes;
+  static constexpr int kSmemBytes = kOffStats + kStatsBytes + 1024 /*align slack*/;
+};
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kNumThreads, 1)
+gemm_ln_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a,
+                       const __grid_constant__ CUtensorMap tmap_b, const GemmLnDev p) {
+  using L = LnCfg<BLOCK_N>;
+  using C = typename L::C;
+  constexpr int kStages = L::kStages;
+  const uint32_t cln = cluster_nctarank();     // CTAs per cluster == column tiles per row panel
+  const uint32_t n_blk = cluster_ctarank();    // this CTA's column tile
+  const int m_blk = static_cast<int>(blockIdx.x / cln);
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * C::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::kOffBars);
+  uint64_t* full_bar = bars;               // [kStages]
+  uint64_t* empty_bar = bars + kStages;    // [kStages]
+  uint64_t* tmem_full_bar = bars + 2 * kStages;
+  uint64_t* stats_bar = bars + 2 * kStages + 1;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + L::kOffVec);
+  float* s_gamma = s_bias + BLOCK_N;
+  float* s_beta = s_gamma + BLOCK_N;
+  float2* s_stats = reinterpret_cast<float2*>(smem + L::kOffStats);   // [cln][128]
+
+  const int warp_idx = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
+  const int num_k_blks = (p.K + BLOCK_K - 1) / BLOCK_K;
+
+  if (warp_idx == 0 && lane == 0) {
+    tma_prefetch_desc(&tmap_a);
+    tma_prefetch_desc(&tmap_b);
+  }
+  if (warp_idx == 1 && lane == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    mbar_init(stats_bar, cln * BLOCK_M);   // one arrival per row-owner thread of every CTA
+    fence_barrier_init();
+  }
+  if (warp_idx == 2) {
+    tmem_alloc(tmem_ptr_smem, BLOCK_N);
+    tmem_relinquish();
+  }
+  tcgen05_fence_before();
+  __syncwarp();
+  cluster_sync_all();   // peers' stats barriers exist before anybody arrives on them
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp_idx == 0) {
+    // ===================================== TMA producer =====================================
+    int stage = 0;
+    uint32_t phase = 0;
+    if (p.wait_flags != nullptr) {
+      if (elect_one_sync()) {
+        const uint32_t target = (*p.wait_epoch) * p.wait_mult;
+        if (!wait_flag_ge(p.wait_flags + m_blk, target, kFlagTimeoutNs)) {
+          if (p.error_flag) atomicExch(p.error_flag, 1);
+        }
+        fence_proxy_async();
+      }
+      __syncwarp();
+    }
+    for (int kb = 0; kb < num_k_blks; ++kb) {
+      mbar_wait(&empty_bar[stage], phase ^ 1);
+      if (elect_one_sync()) {
+        mbar_expect_tx(&full_bar[stage], C::kStageBytes);
+        tma_load_2d(smem_a + stage * C::kABytes, &tmap_a, &full_bar[stage], kb * BLOCK_K,
+                    m_blk * BLOCK_M);
+        tma_load_2d(smem_b + stage * C::kBBytes, &tmap_b, &full_bar[stage], kb * BLOCK_K,
+                    static_cast<int>(n_blk) * BLOCK_N);
+      }
+      __syncwarp();
+      if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp_idx == 1) {
+    // ===================================== MMA issuer ======================================
+    constexpr uint32_t idesc = make_idesc_bf16_f32(BLOCK_M, BLOCK_N, false, false);
+    constexpr uint32_t kadv = (UMMA_K * 2) >> 4;
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < num_k_blks; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tcgen05_fence_after();
+      if (elect_one_sync()) {
+        const uint64_t desc_a = make_smem_desc_sw128(smem_u32(smem_a + stage * C::kABytes), 16, 1024);
+        const uint64_t desc_b = make_smem_desc_sw128(smem_u32(smem_b + stage * C::kBBytes), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          umma_bf16_ss(tmem_base, desc_a + k * kadv, desc_b + k * kadv, idesc,
+                       (kb != 0 || k != 0) ? 1u : 0u);
+        umma_commit(&empty_bar[stage]);
+        if (kb == num_k_blks - 1) umma_commit(tmem_full_bar);
+      }
+      __syncwarp();
+      if (++stage == kStages) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+  } else if (warp_idx >= kEpiWarp0) {
+    // ====================================== epilogue =======================================
+    const int e = warp_idx - kEpiWarp0;
+    const int q = e & 3;
+    const int half = e >> 2;
+    constexpr int HALF_N = BLOCK_N / 2;
+    constexpr int NCH = HALF_N / 32;
+    const int epi_tid = threadIdx.x - kEpiWarp0 * 32;
+    uint8_t* s_out = smem + L::kOffOut;
+    uint8_t* s_stage = s_out + e * (32 * 80);
+    const int row_in_tile = q * 32 + lane;
+    const long long row = static_cast<long long>(m_blk) * BLOCK_M + row_in_tile;
+    const bool row_ok = row < p.M;
+    const int colbase = static_cast<int>(n_blk) * BLOCK_N + half * HALF_N;
+    const bool has_dropout = p.dropout_p > 0.f;
+    const bool has_aux = p.aux != nullptr;
+    uint64_t seed = 0;
+    uint32_t thr16 = 0;
+    float drop_scale = 1.f;
+    if (has_dropout) {
+      seed = dropout_seed(p.rng_state, p.rng_stream);
+      thr16 = static_cast<uint32_t>(p.dropout_p * 65536.f);
+      drop_scale = 1.f / (1.f - p.dropout_p);
+    }
+    for (int i = epi_tid; i < BLOCK_N; i += 256) {
+      const int gc = static_cast<int>(n_blk) * BLOCK_N + i;
+      s_bias[i] = p.bias != nullptr ? __ldg(p.bias + gc) : 0.f;
+      s_gamma[i] = __ldg(p.gamma + gc);
+      s_beta[i] = __ldg(p.beta + gc);
+    }
+    uint4 auxa[4], auxb[4];
+    const __nv_bfloat16* aux_row = has_aux ? p.aux + row * p.ldaux + colbase : nullptr;
+    auto load_aux = [&](uint4 (&dst)[4], int c) {
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        dst[t] = (has_aux && row_ok)
+                     ? *reinterpret_cast<const uint4*>(aux_row + c * 32 + t * 8)
+                     : make_uint4(0, 0, 0, 0);
+    };
+    if (has_aux) load_aux(auxa, 0);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+
+    const long long warp_row0 = static_cast<long long>(m_blk) * BLOCK_M + q * 32;
+    auto store_bf16_chunk = [&](const float (&f)[32], __nv_bfloat16* gout, long long ld, int col0) {
+      uint8_t* mine = s_stage + lane * 80;
+#pragma unroll
+      for (int j = 0; j < 32; j += 8) {
+        uint4 pk;
+        pk.x = pack_bf16x2(f[j], f[j + 1]);
+        pk.y = pack_bf16x2(f[j + 2], f[j + 3]);
+        pk.z = pack_bf16x2(f[j + 4], f[j + 5]);
+        pk.w = pack_bf16x2(f[j + 6], f[j + 7]);
+        *reinterpret_cast<uint4*>(mine + j * 2) = pk;
+      }
+      __syncwarp();
+      const int piece = lane & 3;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int r = i * 8 + (lane >> 2);
+        if (warp_row0 + r < p.M) {
+          const uint4 val = *reinterpret_cast<const uint4*>(s_stage + r * 80 + piece * 16);
+          *reinterpret_cast<uint4*>(gout + (warp_row0 + r) * ld + col0 + piece * 8) = val;
+        }
+      }
+      __syncwarp();
+    };
+
+    mbar_wait(tmem_full_bar, 0);
+    tcgen05_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + half * HALF_N;
+
+    // ---------------- pass 1: z = dropout(acc + bias) + residual; row statistics ----------------
+    float s1 = 0.f, s2 = 0.f;
+    auto pass1 = [&](uint32_t (&v)[32], uint4 (&ax)[4], int c) {
+      const int col0 = colbase + c * 32;
+      float f[32];
+      const float4* sb4 = reinterpret_cast<const float4*>(s_bias + half * HALF_N + c * 32);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 bb = sb4[j >> 2];
+        f[j] = __uint_as_float(v[j]) + bb.x;
+        f[j + 1] = __uint_as_float(v[j + 1]) + bb.y;
+        f[j + 2] = __uint_as_float(v[j + 2]) + bb.z;
+        f[j + 3] = __uint_as_float(v[j + 3]) + bb.w;
+      }
+      if (has_dropout) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          const uint64_t idx4 = (static_cast<uint64_t>(row) * p.N + col0 + j) >> 2;
+          const uint32_t m = dropout_keep4(seed, idx4, thr16);
+          f[j] = (m & 1u) ? f[j] * drop_scale : 0.f;
+          f[j + 1] = (m & 2u) ? f[j + 1] * drop_scale : 0.f;
+          f[j + 2] = (m & 4u) ? f[j + 2] * drop_scale : 0.f;
+          f[j + 3] = (m & 8u) ? f[j + 3] * drop_scale : 0.f;
+        }
+      }
+      if (has_aux) {
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          const uint32_t aw[4] = {ax[t].x, ax[t].y, ax[t].z, ax[t].w};
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float2 x = unpack_bf16x2(aw[u]);
+            f[t * 8 + u * 2] += x.x;
+            f[t * 8 + u * 2 + 1] += x.y;
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        s1 += f[j];
+        s2 = fmaf(f[j], f[j], s2);
+        v[j] = __float_as_uint(f[j]);
+      }
+      tmem_st_32x32b_x32(taddr + c * 32, v);   // park the fp32 sum in the accumulator's columns
+      if (p.z != nullptr)
+        store_bf16_chunk(f, reinterpret_cast<__nv_bfloat16*>(p.z), p.ldz, col0);
+    };
+    {
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
+        if (has_aux) load_aux(auxb, c + 1);
+        pass1(va, auxa, c);
+        tmem_ld_wait();
+        if (c + 2 < NCH) {
+          tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
+          if (has_aux) load_aux(auxa, c + 2);
+        }
+        pass1(vb, auxb, c + 1);
+      }
+      tmem_st_wait();
+    }
+    // ---------------- cluster-wide row statistics through distributed shared memory ----------------
+    // the two column halves of a row live in warps e and e + 4: combine them through the (now
+    // idle) output staging area, then the half-0 thread of each row publishes to every CTA
+    float2* s_half = reinterpret_cast<float2*>(s_out);
+    asm volatile("bar.sync 1, 256;" ::: "memory");   // every warp is done with its staging slice
+    if (half == 1) s_half[row_in_tile] = make_float2(s1, s2);
+    asm volatile("bar.sync 1, 256;" ::: "memory");
+    if (half == 0) {
+      const float2 o = s_half[row_in_tile];
+      s1 += o.x;
+      s2 += o.y;
+      const uint32_t slot = smem_u32(&s_stats[n_blk * BLOCK_M + row_in_tile]);
+      const uint32_t bar = smem_u32(stats_bar);
+      for (uint32_t r = 0; r < cln; ++r) {
+        st_cluster_v2_f32(mapa_shared(slot, r), s1, s2);
+        mbar_arrive_cluster(mapa_shared(bar, r));
+      }
+    }
+    mbar_wait_cluster(stats_bar, 0);
+    float t1 = 0.f, t2 = 0.f;
+    for (uint32_t r = 0; r < cln; ++r) {
+      const float2 o = s_stats[r * BLOCK_M + row_in_tile];
+      t1 += o.x;
+      t2 += o.y;
+    }
+    const float inv_n = 1.f / static_cast<float>(p.N);
+    const float mean = t1 * inv_n;
+    const float var = fmaxf(fmaf(-mean, mean, t2 * inv_n), 0.f);
+    const float rstd = rsqrtf(var + p.eps);
+    if (n_blk == 0 && half == 0 && row_ok) {
+      p.mean[row] = mean;
+      p.rstd[row] = rstd;
+    }
+    // ---------------- pass 2: normalise, gamma / beta, store y (possibly into a peer GPU) ----------------
+    auto pass2 = [&](const uint32_t (&v)[32], int c) {
+      const int col0 = colbase + c * 32;
+      float f[32];
+      const float4* g4 = reinterpret_cast<const float4*>(s_gamma + half * HALF_N + c * 32);
+      const float4* b4 = reinterpret_cast<const float4*>(s_beta + half * HALF_N + c * 32);
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const float4 g = g4[j >> 2], b = b4[j >> 2];
+        f[j] = fmaf((__uint_as_float(v[j]) - mean) * rstd, g.x, b.x);
+        f[j + 1] = fmaf((__uint_as_float(v[j + 1]) - mean) * rstd, g.y, b.y);
+        f[j + 2] = fmaf((__uint_as_float(v[j + 2]) - mean) * rstd, g.z, b.z);
+        f[j + 3] = fmaf((__uint_as_float(v[j + 3]) - mean) * rstd, g.w, b.w);
+      }
+      store_bf16_chunk(f, reinterpret_cast<__nv_bfloat16*>(p.y), p.ldy, col0);
+    };
+    {
+      uint32_t va[32], vb[32];
+      tmem_ld_32x32b_x32(taddr, va);
+#pragma unroll 1
+      for (int c = 0; c < NCH; c += 2) {
+        tmem_ld_wait();
+        tmem_ld_32x32b_x32(taddr + (c + 1) * 32, vb);
+        pass2(va, c);
+        tmem_ld_wait();
+        if (c + 2 < NCH) tmem_ld_32x32b_x32(taddr + (c + 2) * 32, va);
+        pass2(vb, c + 1);
+      }
+    }
+    if (p.signal_flags != nullptr) {
+      // publish this CTA's 128 x BLOCK_N tile of the panel: stores -> fence -> barrier -> one
+      // release.sys; the consumer waits for epoch x (N / BLOCK_N) signals per panel
+      __threadfence_system();
+      asm volatile("bar.sync 2, 256;" ::: "memory");
+      if (epi_tid == 0) red_release_sys_add(p.signal_flags + m_blk, 1u);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncwarp();
+  cluster_sync_all();   // nobody leaves while a peer may still write its statistics into us
+  if (warp_idx == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, BLOCK_N);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -944,8 +1331,99 @@ int dispatch_major(const GemmArgs& a, const GemmDev& dev, cudaStream_t stream) {
 }
 }  // namespace
 
+
+// ---- GEMM + LayerNorm epilogue: tile width, cluster size ----
+int gemm_ln_block_n(int M, int N, bool force) {
+  // 0 = do not run the fused kernel for this shape.  Measured on B200 (profiles/gemm_ln.md):
+  // 256-wide tiles in 4-CTA clusters beat GEMM + standalone LayerNorm by 12 % once the launch
+  // fills the GPU (>= 96 CTAs, i.e. >= 3072 tokens at N = 1024); with fewer tokens the two-kernel
+  // path's 128-wide GEMM tiles use twice as many SMs and win, and 128-wide tiles in 8-CTA clusters
+  // lose outright (at most one such cluster fits a GPC next to another: 29 vs 15 us at 2048
+  // tokens).  `force` (tests, SKY_FUSE_LN=force) accepts every shape the kernel can run.
+  if (M <= 0 || N <= 0 || (N % 128) != 0) return 0;
+  const long long panels = (M + 127) / 128;
+  const bool ok256 = (N % 256) == 0 && N / 256 <= kLnMaxCluster;
+  const bool ok128 = N / 128 <= kLnMaxCluster;
+  if (ok256 && panels * (N / 256) >= 96) return 256;
+  if (!force) return 0;
+  if (ok256) return 256;
+  return ok128 ? 128 : 0;
+}
+int gemm_ln_tiles_per_panel(int M, int N, bool force) {
+  const int bn = gemm_ln_block_n(M, N, force);
+  return bn ? N / bn : 0;
+}
+
+namespace {
+template <int BLOCK_N>
+int launch_ln_inst(const GemmArgs& a, const GemmLnDev& dev, cudaStream_t stream) {
+  using L = LnCfg<BLOCK_N>;
+  using C = typename L::C;
+  CUtensorMap tma, tmb;
+  int rc = make_tmap_bf16_2d(&tma, a.A, a.K, a.M, a.lda, BLOCK_K, BLOCK_M);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&tmb, a.B, a.K, a.N, a.ldb, BLOCK_K, C::kBRows);
+  if (rc) return rc;
+  void (*kern)(CUtensorMap, CUtensorMap, GemmLnDev) = gemm_ln_tcgen05_kernel<BLOCK_N>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         L::kSmemBytes);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    attr_set = true;
+  }
+  const int cln = a.N / BLOCK_N;
+  const int panels = (a.M + BLOCK_M - 1) / BLOCK_M;
+  cudaError_t le = launch_pdl_cluster(kern, dim3(panels * cln), dim3(kNumThreads), L::kSmemBytes,
+                                      stream, cln, tma, tmb, dev);
+  if (le != cudaSuccess) return static_cast<int>(le);
+  return static_cast<int>(cudaGetLastError());
+}
+}  // namespace
+
+int launch_gemm_ln(const GemmArgs& a, cudaStream_t stream) {
+  if (a.M <= 0 || a.N <= 0 || a.K <= 0) return 0;
+  if (a.a_mn || a.b_mn || a.out_f32 || a.accumulate || a.act != ACT_NONE) return 908;
+  if ((a.K % 8) != 0 || (a.lda % 8) != 0 || (a.ldb % 8) != 0) return 902;
+  if (a.ln_gamma == nullptr || a.ln_beta == nullptr || a.ln_mean == nullptr ||
+      a.ln_rstd == nullptr || a.out == nullptr)
+    return 909;
+  if (a.dropout_p > 0.f && a.rng_state == nullptr) return 903;
+  if (a.aux != nullptr && !a.add_aux) return 908;
+  const int bn = a.block_n ? a.block_n : gemm_ln_block_n(a.M, a.N, true);
+  if (bn == 0 || (a.N % bn) != 0 || a.N / bn > kLnMaxCluster) return 907;
+  GemmLnDev d;
+  d.M = a.M;
+  d.N = a.N;
+  d.K = a.K;
+  d.y = a.out;
+  d.ldy = a.ldo;
+  d.z = a.out2;
+  d.ldz = a.ldo2;
+  d.bias = a.bias;
+  d.aux = reinterpret_cast<const __nv_bfloat16*>(a.aux);
+  d.ldaux = a.ldaux;
+  d.gamma = a.ln_gamma;
+  d.beta = a.ln_beta;
+  d.mean = a.ln_mean;
+  d.rstd = a.ln_rstd;
+  d.eps = a.ln_eps;
+  d.dropout_p = a.dropout_p;
+  d.rng_state = a.rng_state;
+  d.rng_stream = a.rng_stream;
+  d.signal_flags = a.signal_flags;
+  d.wait_flags = a.wait_flags;
+  d.wait_epoch = a.wait_epoch;
+  d.wait_mult = a.wait_mult;
+  d.error_flag = a.error_flag;
+  if (bn == 256) return launch_ln_inst<256>(a, d, stream);
+  if (bn == 128) return launch_ln_inst<128>(a, d, stream);
+  return 905;
+}
+
 int launch_gemm(const GemmArgs& a, cudaStream_t stream) {
   if (a.M <= 0 || a.N <= 0 || a.K <= 0) return 0;
+  if (a.ln_gamma != nullptr) return launch_gemm_ln(a, stream);
   if ((a.N % 8) != 0 || (a.K % 8) != 0 || (a.lda % 8) != 0 || (a.ldb % 8) != 0) return 902;
   if (a.a_mn && (a.M % 8) != 0) return 902;
   if (a.dropout_p > 0.f && a.rng_state == nullptr) return 903;

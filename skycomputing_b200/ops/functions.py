@@ -211,12 +211,11 @@ class BertSpanFn(torch.autograd.Function):
             qkv = nat.gemm(x, sp.wqkv.shadow(), bias=sp.bqkv.master(), **wait)
             ctxt, lse = nat.attention_fwd(qkv, mask2, B, S, sp.heads, dropout_p=p_attn, rng=rng,
                                           rng_stream=sp.rng_base + 1)
-            z1 = nat.gemm(ctxt, sp.wo.shadow(), bias=sp.bo.master(), aux=x, add_aux=True,
-                          dropout_p=p_hid, rng=rng, rng_stream=sp.rng_base + 2)
             ln_out = {}
             if out_ch is not None and not sp.has_body:
                 ln_out = dict(y_ptr=out_ch.peer_act_ptr(mb_out), signal_flags=out_ch.peer_act_flags_ptr(mb_out))
-            y1, mean1, rstd1 = _ln_fwd(z1, sp.g1.master(), sp.b1n.master(), sp.eps, **ln_out)
+            y1, z1, mean1, rstd1 = _gemm_ln(ctxt, sp.wo, sp.bo, x, sp.g1, sp.b1n, sp.eps, p_hid, rng,
+                                            sp.rng_base + 2, ln_out)
             saved.update(x=x, mask2=mask2, qkv=qkv, ctxt=ctxt, lse=lse, z1=z1, mean1=mean1,
                          rstd1=rstd1)
             a = y1
@@ -242,12 +241,11 @@ class BertSpanFn(torch.autograd.Function):
             inter = _flat2d(inputs[0])
         if sp.has_tail:
             wait = _ch_kwargs_wait(in_ch, mb_in) if (in_ch is not None and not sp.has_body) else {}
-            z2 = nat.gemm(inter, sp.w2.shadow(), bias=sp.b2.master(), aux=a, add_aux=True,
-                          dropout_p=p_hid, rng=rng, rng_stream=sp.rng_base + 3, **wait)
             ln_out = {}
             if out_ch is not None:
                 ln_out = dict(y_ptr=out_ch.peer_act_ptr(mb_out), signal_flags=out_ch.peer_act_flags_ptr(mb_out))
-            y2, mean2, rstd2 = _ln_fwd(z2, sp.g2.master(), sp.b2n.master(), sp.eps, **ln_out)
+            y2, z2, mean2, rstd2 = _gemm_ln(inter, sp.w2, sp.b2, a, sp.g2, sp.b2n, sp.eps, p_hid, rng,
+                                            sp.rng_base + 3, ln_out, **wait)
             saved.update(z2=z2, mean2=mean2, rstd2=rstd2)
         if sp.has_body or sp.has_tail:
             saved.update(a=a, inter=inter)
@@ -445,6 +443,26 @@ def _wgrad(g: torch.Tensor, act: torch.Tensor, wbank: ParamBank,
 def _dummy_out(like: torch.Tensor) -> torch.Tensor:
     """Stand-in output for spans whose real output was written into the next stage's HBM."""
     return torch.zeros(1, dtype=torch.bfloat16, device=like.device)
+
+
+def _gemm_ln(a, wbank, bbank, residual, gbank, betabank, eps, p_drop, rng, rng_stream,
+             ln_out: dict, **wait):
+    """Dense + bias + dropout + residual + LayerNorm (the reference's BertSelfOutput / BertOutput,
+    scaelum/model/bert_layers.py:285-289,323-327).  ONE tcgen05 kernel with the LayerNorm in the
+    GEMM epilogue whenever the row fits a thread-block cluster; with ``ln_out`` (peer pointer + panel
+    flags of a fused stage boundary) that kernel stores y straight into the next stage's HBM.  Otherwise GEMM, then the standalone LayerNorm.
+    Returns (y | None, z, mean, rstd)."""
+    M, N = a.shape[0], wbank.master().shape[0]
+    # both ends of a fused boundary evaluate the same predicate on the same (rows, cols): the
+    # consumer's expected signal count per panel follows from it (parallel/p2p.py)
+    if nat.gemm_ln_supported(M, N):
+        return nat.gemm_ln(a, wbank.shadow(), gbank.master(), betabank.master(), eps=eps,
+                           bias=bbank.master(), residual=residual, dropout_p=p_drop, rng=rng,
+                           rng_stream=rng_stream, y_ld=N, **ln_out, **wait)
+    z = nat.gemm(a, wbank.shadow(), bias=bbank.master(), aux=residual, add_aux=True,
+                 dropout_p=p_drop, rng=rng, rng_stream=rng_stream, **wait)
+    y, mean, rstd = _ln_fwd(z, gbank.master(), betabank.master(), eps, **ln_out)
+    return y, z, mean, rstd
 
 
 def _ln_fwd(z, gamma, beta, eps, y_ptr: int = 0, signal_flags: int = 0):

@@ -204,6 +204,75 @@ def gemm(
     return out
 
 
+def _fuse_ln_mode() -> str:
+    import os
+
+    return os.environ.get("SKY_FUSE_LN", "1")
+
+
+def gemm_ln_supported(M: int, N: int) -> bool:
+    """Should ``dense + LayerNorm`` of this output shape run as the one-kernel GEMM + LayerNorm
+    epilogue?  Default: where it is faster than GEMM + standalone LayerNorm (csrc: gemm_ln_block_n);
+    ``SKY_FUSE_LN=force``: wherever the kernel can run; ``SKY_FUSE_LN=0``: never."""
+    mode = _fuse_ln_mode()
+    if mode == "0":
+        return False
+    return ext().gemm_ln_block_n(int(M), int(N), mode == "force") != 0
+
+
+def gemm_ln_tiles_per_panel(M: int, N: int) -> int:
+    """Flag signals per 128-row panel when the fused kernel writes a stage boundary."""
+    return ext().gemm_ln_tiles_per_panel(int(M), int(N), _fuse_ln_mode() == "force")
+
+
+def gemm_ln(a: torch.Tensor, b: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *,
+            eps: float = 1e-12, bias: Optional[torch.Tensor] = None,
+            residual: Optional[torch.Tensor] = None, dropout_p: float = 0.0,
+            rng: Optional[RngState] = None, rng_stream: int = 0, save_z: bool = True,
+            y_ptr: int = 0, y_ld: int = 0, signal_flags: int = 0, wait_flags: int = 0,
+            wait_epoch: int = 0, wait_mult: int = 0, error_flag: int = 0, block_n: int = 0):
+    """y = LayerNorm(dropout(a b^T + bias) + residual) * gamma + beta in ONE tcgen05 kernel
+    (cluster-wide row statistics through DSMEM, see csrc/kernels/gemm_sm100.cu).
+
+    Returns ``(y, z, mean, rstd)``: ``z`` is the bf16 pre-LayerNorm sum saved for backward (None
+    when ``save_z`` is False), ``y`` is None when ``y_ptr`` redirects the store to raw (peer)
+    memory; ``signal_flags`` then receives ``gemm_ln_tiles_per_panel`` signals per 128-row panel."""
+    _check(a, torch.bfloat16, "a")
+    _check(b, torch.bfloat16, "b")
+    _check(gamma, torch.float32, "gamma")
+    _check(beta, torch.float32, "beta")
+    M, K = a.shape
+    N, Kb = b.shape
+    if K != Kb:
+        raise ValueError(f"inner dimensions differ: {K} vs {Kb}")
+    if bias is not None:
+        _check(bias, torch.float32, "bias")
+    if residual is not None:
+        _check(residual, torch.bfloat16, "residual")
+    dev = a.device
+    y = None
+    if y_ptr:
+        o_ptr, ldo = y_ptr, (y_ld or N)
+    else:
+        y = torch.empty((M, N), dtype=torch.bfloat16, device=dev)
+        o_ptr, ldo = y.data_ptr(), N
+    z = torch.empty((M, N), dtype=torch.bfloat16, device=dev) if save_z else None
+    mean = torch.empty(M, dtype=torch.float32, device=dev)
+    rstd = torch.empty(M, dtype=torch.float32, device=dev)
+    ext().gemm(
+        A=a.data_ptr(), B=b.data_ptr(), M=M, N=N, K=K, lda=a.stride(0), ldb=b.stride(0),
+        out=o_ptr, ldo=ldo, out2=_ptr(z), ldo2=0 if z is None else N, bias=_ptr(bias),
+        aux=_ptr(residual), ldaux=0 if residual is None else residual.stride(0),
+        add_aux=residual is not None, dropout_p=float(dropout_p),
+        rng_state=0 if rng is None else rng.ptr, rng_stream=rng_stream,
+        signal_flags=signal_flags, wait_flags=wait_flags, wait_epoch=wait_epoch,
+        wait_mult=wait_mult, error_flag=error_flag, block_n=block_n,
+        ln_gamma=gamma.data_ptr(), ln_beta=beta.data_ptr(), ln_mean=mean.data_ptr(),
+        ln_rstd=rstd.data_ptr(), ln_eps=float(eps), stream=_stream(),
+    )
+    return y, z, mean, rstd
+
+
 def layernorm_fwd(z, gamma, beta, eps: float = 1e-12, *, y=None, wait_flags: int = 0,
                   wait_epoch: int = 0, wait_mult: int = 0, error_flag: int = 0):
     _check(z, torch.bfloat16, "z")

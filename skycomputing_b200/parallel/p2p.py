@@ -6,8 +6,9 @@ Every pipeline rank owns, in ITS OWN HBM and mapped by its neighbours through CU
   ``[B_mb*S]`` fp32 mask slot per micro-batch) with one ``uint32`` flag per 128-row panel,
 * an inbound GRADIENT region written by the next stage, same shape, own flags.
 
-Producers are kernels of the neighbour GPU: the last LayerNorm of stage *i* stores its output rows
-straight into stage *i+1*'s activation slot, and the first dgrad GEMM of stage *i+1*
+Producers are kernels of the neighbour GPU: the last GEMM of stage *i* (FFN2 with bias + dropout +
+residual + LayerNorm in its tcgen05 epilogue) stores its output tiles straight into stage *i+1*'s
+activation slot, and the first dgrad GEMM of stage *i+1*
 (``QKV-dgrad + residual``) stores its output tiles straight into stage *i*'s gradient slot; both
 bump the panel flags with ``red.release.sys``.  Consumers (the QKV GEMM's TMA producer warp / the
 LayerNorm-backward warps) poll the flags with ``ld.acquire.sys``.  Flags are cumulative and never
@@ -225,9 +226,14 @@ class FusedBoundaryManager:
             self._regions.append(self.next.local)
         block_n = ext.gemm_pick_block_n(rows, cols)
         grad_mult = ext.gemm_tiles_per_panel(cols, block_n)
+        # forward producer = the GEMM + LayerNorm kernel (one signal per column tile of a panel)
+        # when the row fits a cluster, else the standalone LayerNorm kernel (one per 8 rows)
+        act_mult = (nat.gemm_ln_tiles_per_panel(rows, cols) if nat.gemm_ln_supported(rows, cols)
+                    else ext.LN_SIGNALS_PER_PANEL)
         for ch in (self.prev, self.next):
             if ch is not None:
                 ch.grad_wait_mult = grad_mult
+                ch.act_wait_mult = act_mult
                 ch.rows, ch.cols = rows, cols
         # exchange handles: everybody publishes {to_prev: handle of my act region, to_next: grad}
         mine: Dict[str, object] = {"rank": my_rank, "gpu": self._gpu_uuid(device)}

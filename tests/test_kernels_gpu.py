@@ -279,3 +279,98 @@ def test_gemm_stream_k_fused_epilogue(nat):
     res = _rand(M, N)
     out = nat.gemm(a, b, bias=bias, aux=res, add_aux=True, stream_k=1, pair=1)
     _close(out, h + res.float())
+
+
+# ------------------------------------------------------------------------------------------
+# GEMM + bias + dropout + residual + LayerNorm in one kernel (cluster-wide row statistics)
+# ------------------------------------------------------------------------------------------
+def _ln_ref(zf, gamma, beta, eps=1e-12):
+    mu = zf.mean(-1, keepdim=True)
+    var = ((zf - mu) ** 2).mean(-1, keepdim=True)
+    return (zf - mu) / torch.sqrt(var + eps) * gamma + beta, mu.squeeze(-1), (1 / torch.sqrt(var + eps)).squeeze(-1)
+
+
+@pytest.mark.parametrize("M,N,K,block_n", [
+    (4096, 1024, 1024, 0),      # BERT-large attention output projection: 4-CTA clusters, 256-wide
+    (2048, 1024, 4096, 0),      # BERT-large FFN2 at 16 sequences: 8-CTA clusters, 128-wide
+    (4096, 1024, 4096, 256),
+    (512, 256, 512, 0),         # 2-CTA clusters
+    (300, 256, 192, 128),       # ragged M
+    (128, 128, 64, 128),        # a cluster of one
+    (256, 768, 256, 0),         # 3 / 6 CTAs per cluster (not a power of two)
+])
+def test_gemm_layernorm_epilogue(nat, M, N, K, block_n):
+    torch.manual_seed(11)
+    assert nat.ext().gemm_ln_block_n(M, N, True) != 0
+    # the automatic policy only fuses launches that fill the GPU with 256-wide tiles
+    assert nat.gemm_ln_supported(M, N) == (N % 256 == 0 and ((M + 127) // 128) * (N // 256) >= 96)
+    a, w = _rand(M, K), _rand(N, K, scale=0.05)
+    bias = torch.randn(N, device="cuda") * 0.1
+    res = _rand(M, N)
+    gamma = 1.0 + 0.1 * torch.randn(N, device="cuda")
+    beta = 0.1 * torch.randn(N, device="cuda")
+    y, z, mean, rstd = nat.gemm_ln(a, w, gamma, beta, bias=bias, residual=res, block_n=block_n)
+    zf = a.float() @ w.float().t() + bias + res.float()
+    yr, mur, rstdr = _ln_ref(zf, gamma, beta)
+    _close(z, zf)
+    _close(y, yr, rtol=2e-2, atol=3e-2)
+    torch.testing.assert_close(mean, mur, rtol=1e-3, atol=2e-3)
+    torch.testing.assert_close(rstd, rstdr, rtol=2e-3, atol=1e-4)
+    # and against the two-kernel path it replaces (same bf16 rounding points except the stats)
+    z2 = nat.gemm(a, w, bias=bias, aux=res, add_aux=True)
+    y2, mean2, rstd2 = nat.layernorm_fwd(z2, gamma, beta)
+    assert torch.equal(z, z2)
+    _close(y, y2, rtol=1e-2, atol=2e-2)
+
+
+def test_gemm_layernorm_epilogue_dropout_uses_the_gemm_mask(nat):
+    torch.manual_seed(12)
+    M, N, K, p = 512, 1024, 256, 0.1
+    rng = nat.RngState(99)
+    a, w = _rand(M, K), _rand(N, K, scale=0.05)
+    bias = torch.randn(N, device="cuda") * 0.1
+    res = _rand(M, N)
+    gamma, beta = torch.ones(N, device="cuda"), torch.zeros(N, device="cuda")
+    # the mask of (rng, stream 5) for an [M, N] output, read off a GEMM of zeros + bias 1
+    probe = nat.gemm(torch.zeros(M, 64, dtype=torch.bfloat16, device="cuda"),
+                     torch.zeros(N, 64, dtype=torch.bfloat16, device="cuda"),
+                     bias=torch.ones(N, device="cuda"), dropout_p=p, rng=rng, rng_stream=5).float()
+    keep = probe != 0
+    y, z, mean, rstd = nat.gemm_ln(a, w, gamma, beta, bias=bias, residual=res, dropout_p=p,
+                                   rng=rng, rng_stream=5)
+    h = a.float() @ w.float().t() + bias
+    zf = torch.where(keep, h / (1 - p), torch.zeros_like(h)) + res.float()
+    _close(z, zf)
+    _close(y, _ln_ref(zf, gamma, beta)[0], rtol=2e-2, atol=3e-2)
+    # LayerNorm backward regenerates the same mask from (rng, stream)
+    dy = _rand(M, N)
+    dz, dzd = nat.layernorm_bwd(dy, z, mean, rstd, gamma, None, None, dropout_p=p, rng=rng,
+                                rng_stream=5)
+    _close(dzd, torch.where(keep, dz.float() / (1 - p), torch.zeros_like(dz.float())))
+
+
+def test_gemm_layernorm_epilogue_signals_panels_like_a_stage_boundary(nat):
+    """y redirected to a raw pointer + panel flags (single GPU stand-in for the peer slot): every
+    128-row panel receives gemm_ln_tiles_per_panel signals; a consumer GEMM gated on those flags
+    reads the complete tensor."""
+    torch.manual_seed(13)
+    M, N, K = 1024, 1024, 512
+    a, w = _rand(M, K), _rand(N, K, scale=0.05)
+    gamma, beta = torch.ones(N, device="cuda"), torch.zeros(N, device="cuda")
+    slot = torch.zeros(M, N, dtype=torch.bfloat16, device="cuda")
+    flags = torch.zeros(M // 128, dtype=torch.int32, device="cuda")
+    epoch = torch.ones(1, dtype=torch.int32, device="cuda")
+    err = torch.zeros(1, dtype=torch.int32, device="cuda")
+    mult = nat.ext().gemm_ln_tiles_per_panel(M, N, True)
+    assert mult == 4
+    y, z, _, _ = nat.gemm_ln(a, w, gamma, beta, y_ptr=slot.data_ptr(), y_ld=N,
+                             signal_flags=flags.data_ptr())
+    assert y is None
+    w2 = _rand(256, N, scale=0.05)
+    out = nat.gemm(slot, w2, wait_flags=flags.data_ptr(), wait_epoch=epoch.data_ptr(),
+                   wait_mult=mult, error_flag=err.data_ptr())
+    torch.cuda.synchronize()
+    assert flags.tolist() == [mult] * (M // 128) and int(err.item()) == 0
+    yr = _ln_ref(z.float(), gamma, beta)[0]
+    _close(slot, yr, rtol=2e-2, atol=3e-2)
+    _close(out, slot.float() @ w2.float().t(), atol=0.3)

@@ -215,3 +215,22 @@ def test_overwrite_first_gradients_match_zeroed_gradients():
         assert diff < 1e-4, diff
     finally:
         set_backend("auto")
+
+
+def test_full_block_with_the_layernorm_fused_into_the_gemm(monkeypatch):
+    """SKY_FUSE_LN=force: dense + bias + dropout + residual + LayerNorm of the attention output
+    and of FFN2 run as ONE tcgen05 kernel each (2-CTA clusters at hidden 256) instead of the
+    automatic policy's GEMM + standalone LayerNorm for launches this small."""
+    from skycomputing_b200.ops import native as nat
+
+    monkeypatch.setenv("SKY_FUSE_LN", "force")
+    assert nat.gemm_ln_supported(3 * 128, 256)
+    nat.enable_launch_counter()
+    before = nat.launch_count()
+    cfg = _cfg()
+    _run_pair(["BertLayer_Head", "BertLayer_Body", "BertLayer_Tail"], _hidden_inputs(cfg), cfg)
+    fused_launches = nat.launch_count() - before
+    monkeypatch.setenv("SKY_FUSE_LN", "0")
+    before = nat.launch_count()
+    _run_pair(["BertLayer_Head", "BertLayer_Body", "BertLayer_Tail"], _hidden_inputs(cfg), cfg)
+    assert (nat.launch_count() - before) - fused_launches == 2    # two LayerNorm launches gone
