@@ -157,11 +157,20 @@ def test_native_block_matches_reference_classes_at_bert_large_geometry():
     worst = {}
     for (ref, ours) in pairs:
         for (n, pr), (_, po) in zip(ref.named_parameters(), ours.named_parameters()):
-            if pr.grad.abs().max() < 1e-6 * max(1.0, float(cot.abs().max())):
-                continue                       # key bias: mathematically zero gradient
+            if n.endswith("key.bias"):
+                _check_zero_gradient(ours, po)
+                continue
             worst[n] = max(worst.get(n, 0.0), _rel_l2(po.grad, pr.grad))
     bad = {n: e for n, e in worst.items() if e > 3e-2}
     assert not bad, bad
+
+
+def _check_zero_gradient(layer, key_bias):
+    """The key bias has a mathematically ZERO gradient (softmax is invariant to a per-query shift
+    of all scores): the reference leaves fp32 round-off there, the bf16 path leaves bf16 round-off;
+    require it to be small against the query-bias gradient instead of comparing noise to noise."""
+    q = dict(layer.named_parameters())["attention.self.query.bias"].grad
+    assert float(key_bias.grad.abs().max()) < 0.1 * float(q.abs().max())
 
 
 class _FixedMaskDropout(torch.nn.Module):
@@ -226,6 +235,7 @@ def test_exact_dropout_mask_parity_with_reference_classes():
     assert _rel_l2(xn.grad, xr.grad) < 2.5e-2
     for (ref, ours) in pairs:
         for (n, pr), (_, po) in zip(ref.named_parameters(), ours.named_parameters()):
-            if pr.grad.abs().max() < 1e-6:
+            if n.endswith("key.bias"):
+                _check_zero_gradient(ours, po)
                 continue
             assert _rel_l2(po.grad, pr.grad) < 3e-2, (n, _rel_l2(po.grad, pr.grad))
