@@ -39,7 +39,10 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference"])
+    # b1 = the reference's own layer classes + NCCL p2p (baseline/run_b1.py), fp32 or bf16-autocast
+    ap.add_argument("--impl", type=str, default="ours", choices=["ours", "reference", "b1"])
+    ap.add_argument("--b1-dtype", type=str, default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--b1-micro-batches", type=int, default=1)
     # `optimal` = the framework's exact load-balancing allocator over device benchmarks (the
     # capability under test); `even` is the reference's baseline split for comparison
     ap.add_argument("--alloc", type=str, default=os.environ.get("SKY_ALLOC", "optimal"),
@@ -137,8 +140,41 @@ def run_ours(args) -> dict:
         result = measure(args, plain, rank, world, local_rank, device)
         if result == "fallback":
             result = None
+    b1 = measure_b1(args, world)
+    if result is not None and b1:
+        result["vs_b1"] = {
+            k: dict(b1_value=v["value"], b1_ms_per_step=v["ms_per_step"],
+                    ratio=result["value"] / v["value"], b1_config=v["config"])
+            for k, v in b1.items() if "value" in v}
+        result["vs_b1"]["note"] = (
+            "B1 = the reference's own layer classes + even split, NCCL send/recv boundaries "
+            "(baseline/run_b1.py), measured in this process right after our timed region; "
+            "bf16 = torch.autocast(bfloat16), the same-precision comparison for our bf16 kernels; "
+            "fp32 = the reference's precision (our arm is bf16: not like for like)")
     dist.destroy_process_group()
     return result
+
+
+def measure_b1(args, world) -> dict:
+    """Same-box, same-process B1 numbers for the `vs_b1` block (SKY_BENCH_B1=0 skips them)."""
+    if os.environ.get("SKY_BENCH_B1", "1") == "0":
+        return {}
+    out = {}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import run_b1
+
+        m = max(1, args.gpus)          # give the baseline pipelining too (GPipe micro-batches)
+        out["bf16"] = run_b1.run_in_process(args.gpus, steps=8, warmup=3, dtype="bf16",
+                                            micro_batches=m, layer_num=args.layers)
+        out["fp32"] = run_b1.run_in_process(args.gpus, steps=4, warmup=3, dtype="fp32",
+                                            micro_batches=m, layer_num=args.layers)
+    except Exception as e:  # the baseline must never take our measurement down
+        import traceback
+
+        traceback.print_exc()
+        out["error"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+    return out
 
 
 def pick_plan(args) -> dict:
@@ -318,6 +354,26 @@ def measure(args, plan, rank, world, local_rank, device):
     else:
         launches = int(graph_launches)
     err = eng.fused.error_code() if eng.fused is not None else 0
+    # exposed stage-boundary communication (part of the BASELINE.json metric): per-crossing cost
+    # of both fused boundary kernels, measured on ranks 0 / 1 right here, times the crossings a
+    # rank has on its critical path per step
+    boundary = None
+    # (eng.fused is created collectively: the same verdict on every rank)
+    if world > 1 and eng.fused is not None and os.environ.get("SKY_BENCH_BOUNDARY", "1") != "0":
+        try:
+            from skycomputing_b200.utils.boundary_probe import probe
+
+            rows = probe(mb * SEQ_LEN)
+            chunks = max(1, virtual_stages)
+            per_cross = sum(r["exposed_us"] for r in rows.values())
+            boundary = dict(
+                exposed_boundary_ms_per_step=round(micro_batches * chunks * per_cross * 1e-3, 4),
+                crossings_per_rank_and_step=micro_batches * chunks, per_crossing=rows,
+                note="exposed = boundary kernel with peer stores + flags minus the same kernel "
+                     "with local stores (CUDA-graph replays, both directions concurrently); "
+                     "roofline = max(local compute, bytes / 900 GB/s)")
+        except Exception as e:  # diagnostics must not take the measurement down
+            boundary = dict(unavailable=f"{type(e).__name__}: {e}"[:200])
     if os.environ.get("SKY_TRACE", "0") == "1":
         _dump_trace(eng, rank, world, device, N)
     result = None
@@ -353,7 +409,7 @@ def measure(args, plan, rank, world, local_rank, device):
                             "memory, graph replay, async D2H of the loss into pinned memory (read "
                             "by the host one step later; the last one before the timer stops)"},
             "gpu_launches": launches, "clocks": clocks, "final_loss": last_loss,
-            "flag_wait_errors": err,
+            "flag_wait_errors": err, "boundary": boundary,
         }
     eng.close()
     return result
@@ -405,6 +461,15 @@ def main():
 
             traceback.print_exc()
             out = {"impl": "reference", "unavailable": f"{type(e).__name__}: {e}"[:300]}
+        if int(os.environ.get("RANK", "0")) == 0:
+            print(json.dumps(out), flush=True)
+        return 0
+    if args.impl == "b1":
+        sys.path.insert(0, os.path.join(ROOT, "baseline"))
+        import run_b1
+
+        out = run_b1.run(args.gpus, args.steps, args.warmup, args.b1_dtype, args.b1_micro_batches,
+                         args.layers)
         if int(os.environ.get("RANK", "0")) == 0:
             print(json.dumps(out), flush=True)
         return 0
