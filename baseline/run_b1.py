@@ -105,12 +105,35 @@ def run_in_process(n_gpus: int, steps: int, warmup: int, dtype: str = "bf16",
         batches.append((ids.pin_memory(), torch.zeros_like(ids).pin_memory(),
                         torch.ones_like(ids).pin_memory(),
                         torch.randint(0, 3, (global_batch,), generator=g).pin_memory()))
-    hidden = 1024
-
     def fwd(args):
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
             out = stage(*args)
         return out if isinstance(out, (tuple, list)) else (out,)
+
+    def diff_flags(n):
+        # every floating boundary tensor carries a gradient except a trailing attention mask
+        return [i < n - 1 or n == 1 for i in range(n)]
+
+    # ---- shape propagation: the reference's even split may cut INSIDE a transformer block (after
+    # BertLayer_Head: 2 tensors, after BertLayer_Body: 3 tensors of different widths), so every
+    # stage learns the layout of its inputs from a dry run of the stage in front of it
+    in_meta = None
+    for r in range(n_gpus):
+        box = [None]
+        if rank == r:
+            if first:
+                probe = tuple(t[:mb].to(device) for t in batches[0][:3])
+            else:
+                probe = tuple(torch.zeros(shape, device=device, dtype=act_dtype) for shape in in_meta)
+            with torch.no_grad():
+                outs = fwd(probe)
+            box = [[tuple(o.shape) for o in outs]]
+            del outs, probe
+        if n_gpus > 1:
+            dist.broadcast_object_list(box, src=r, group=group)
+        if rank == r + 1:
+            in_meta = box[0]
+    torch.cuda.empty_cache()
 
     def step(i: int):
         ids, tt, am, labels = (t.to(device, non_blocking=True) for t in batches[i % 4])
@@ -121,34 +144,43 @@ def run_in_process(n_gpus: int, steps: int, warmup: int, dtype: str = "bf16",
             if first:
                 args = (ids[sl], tt[sl], am[sl])
             else:
-                x = torch.empty(mb, seq_len, hidden, device=device, dtype=act_dtype)
-                mask = torch.empty(mb, 1, 1, seq_len, device=device, dtype=act_dtype)
-                dist.recv(x, rank - 1, group=group)
-                dist.recv(mask, rank - 1, group=group)
-                x.requires_grad_(True)
-                args = (x, mask)
+                args = []
+                for shape, d in zip(in_meta, diff_flags(len(in_meta))):
+                    t = torch.empty(shape, device=device, dtype=act_dtype)
+                    dist.recv(t, rank - 1, group=group)
+                    args.append(t.requires_grad_(True) if d else t)
+                args = tuple(args)
             outs = fwd(args)
             if last:
                 loss = loss_fn(outs[0].float(), labels[sl]) / m
-                saved.append((args, loss))
+                saved.append((args, (loss,)))
             else:
-                # the boundary tensor travels in the compute dtype (bf16 under autocast, where
+                # boundary tensors travel in the compute dtype (bf16 under autocast, where
                 # LayerNorm itself returns fp32): a differentiable cast keeps autograd intact
-                y = outs[0].to(act_dtype)
-                dist.send(y.detach().contiguous(), rank + 1, group=group)
-                dist.send(outs[1].detach().to(act_dtype).contiguous(), rank + 1, group=group)
-                saved.append((args, y))
+                ys = tuple(o.to(act_dtype) for o in outs)
+                for y in ys:
+                    dist.send(y.detach().contiguous(), rank + 1, group=group)
+                saved.append((args, ys))
         for j in range(m):                                       # ---- backwards
-            args, out = saved[j]
+            args, outs = saved[j]
             if last:
-                out.backward()
-                loss_val = out.detach() if loss_val is None else loss_val + out.detach()
+                outs[0].backward()
+                loss_val = outs[0].detach() if loss_val is None else loss_val + outs[0].detach()
             else:
-                gout = torch.empty_like(out)
-                dist.recv(gout, rank + 1, group=group)
-                out.backward(gout)
+                ts, gs = [], []
+                for y, d in zip(outs, diff_flags(len(outs))):
+                    if d:
+                        gout = torch.empty_like(y)
+                        dist.recv(gout, rank + 1, group=group)
+                        if y.requires_grad:
+                            ts.append(y)
+                            gs.append(gout)
+                torch.autograd.backward(ts, gs)
             if not first:
-                dist.send(args[0].grad.contiguous(), rank - 1, group=group)
+                for a, d in zip(args, diff_flags(len(args))):
+                    if d:
+                        g_in = a.grad if a.grad is not None else torch.zeros_like(a)
+                        dist.send(g_in.contiguous(), rank - 1, group=group)
         opt.step()
         opt.zero_grad(set_to_none=True)
         return loss_val

@@ -140,12 +140,13 @@ def run_ours(args) -> dict:
         result = measure(args, plain, rank, world, local_rank, device)
         if result == "fallback":
             result = None
-    b1 = measure_b1(args, world)
+    b1 = measure_b1(args, world, rank)
     if result is not None and b1:
         result["vs_b1"] = {
             k: dict(b1_value=v["value"], b1_ms_per_step=v["ms_per_step"],
                     ratio=result["value"] / v["value"], b1_config=v["config"])
             for k, v in b1.items() if "value" in v}
+        result["vs_b1"].update({k: v for k, v in b1.items() if "value" not in v})
         result["vs_b1"]["note"] = (
             "B1 = the reference's own layer classes + even split, NCCL send/recv boundaries "
             "(baseline/run_b1.py), measured in this process right after our timed region; "
@@ -155,25 +156,58 @@ def run_ours(args) -> dict:
     return result
 
 
-def measure_b1(args, world) -> dict:
-    """Same-box, same-process B1 numbers for the `vs_b1` block (SKY_BENCH_B1=0 skips them)."""
+def measure_b1(args, world, rank) -> dict:
+    """Same-box B1 numbers for the `vs_b1` block, measured right after our timed region.
+
+    B1 runs in a CHILD process group (its own torchrun) under a hard timeout: whatever the
+    baseline does - including hanging in a mismatched send / recv - it cannot take our own
+    measurement down.  Our ranks have released their engines and wait on the rendezvous store (no
+    NCCL kernel spins on the GPUs meanwhile).  SKY_BENCH_B1=0 skips it."""
     if os.environ.get("SKY_BENCH_B1", "1") == "0":
         return {}
+    import torch.distributed as dist
+
+    N = args.gpus
     out = {}
-    try:
-        sys.path.insert(0, os.path.join(ROOT, "baseline"))
-        import run_b1
+    if rank == 0:
+        env = {k: v for k, v in os.environ.items()
+               if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_PORT", "GROUP_RANK",
+                            "LOCAL_WORLD_SIZE", "ROLE_RANK", "ROLE_WORLD_SIZE", "TORCHELASTIC_RUN_ID")}
+        port = int(os.environ.get("MASTER_PORT", "29533")) + 17
+        for dtype, steps in (("bf16", 8), ("fp32", 4)):
+            tail = [os.path.join(ROOT, "bench.py"), "--impl", "b1", "--gpus", str(N), "--steps",
+                    str(steps), "--warmup", "3", "--b1-dtype", dtype, "--b1-micro-batches", str(N),
+                    "--layers", str(args.layers)]
+            if N > 1:
+                cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1",
+                       f"--nproc-per-node={N}", "--master-addr", "127.0.0.1", "--master-port",
+                       str(port)] + tail
+            else:
+                cmd = [sys.executable] + tail
+            proc = None
+            try:
+                proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                        text=True, env=env, start_new_session=True)
+                stdout, _ = proc.communicate(timeout=240)
+                line = [l for l in stdout.splitlines() if l.startswith("{")][-1]
+                out[dtype] = json.loads(line)
+            except subprocess.TimeoutExpired:
+                import signal
 
-        m = max(1, args.gpus)          # give the baseline pipelining too (GPipe micro-batches)
-        out["bf16"] = run_b1.run_in_process(args.gpus, steps=8, warmup=3, dtype="bf16",
-                                            micro_batches=m, layer_num=args.layers)
-        out["fp32"] = run_b1.run_in_process(args.gpus, steps=4, warmup=3, dtype="fp32",
-                                            micro_batches=m, layer_num=args.layers)
-    except Exception as e:  # the baseline must never take our measurement down
-        import traceback
+                os.killpg(proc.pid, signal.SIGKILL)      # the session we started, nothing else
+                proc.wait()
+                out[dtype] = {"unavailable": "B1 timed out after 240 s"}
+            except Exception as e:
+                out[dtype] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            port += 1
+    if world > 1:
+        store = dist.distributed_c10d._get_default_store()
+        if rank == 0:
+            store.set("sky_b1_done", "1")
+        else:
+            from datetime import timedelta
 
-        traceback.print_exc()
-        out["error"] = {"unavailable": f"{type(e).__name__}: {e}"[:300]}
+            store.wait(["sky_b1_done"], timedelta(seconds=700))
     return out
 
 
