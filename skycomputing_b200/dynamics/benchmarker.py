@@ -83,7 +83,12 @@ class DeviceBenchmarker(BaseBenchmarker):
         t, free_mib = nat.ext().device_benchmark(
             tokens=block_shape["tokens"], hidden=block_shape["hidden"],
             intermediate=block_shape["intermediate"], iterations=iterations,
-            warmup=max(warmup, 1), slowdown=float(cfg.get("slowdown", 0) or 0))
+            warmup=max(warmup, 1), slowdown=float(cfg.get("slowdown", 0) or 0),
+            # the proxy is the block's real forward + backward kernel chain (GEMMs, attention,
+            # LayerNorm, reductions); "gemm_only" selects round 1's four forward GEMMs
+            mode=1 if block_shape.get("proxy_kernels") == "gemm_only" else 0,
+            seq=int(block_shape.get("seq", 128)),
+            heads=int(block_shape.get("heads", max(1, block_shape["hidden"] // 64))))
         mem_limit = cfg.get("mem_limit", -1)
         return t, (mem_limit if mem_limit and mem_limit > 0 else free_mib - 500)
 
