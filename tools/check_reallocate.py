@@ -45,7 +45,8 @@ def main():
     wm = sky.WorkerManager(first_rank=0)
     wm.load_worker_pool_from_config(workers)
     wm = sky.Allocator(model_config, wm, granularity="block").even_allocate()
-    layers_before = [len(w.model_config) for w in wm.worker_pool]
+    layers_before = [sum(len(w.model_config) for w in wm.worker_pool if w.device == d)
+                     for d in range(world)]
     model = sky.RpcModel(wm, this_rank=rank)
     optim_cfg = dict(optim_type="SGD", lr=1e-3)
     opt = sky.build_optimizer(model.optim_module, dict(optim_cfg))
@@ -86,7 +87,10 @@ def main():
     torch.cuda.synchronize()
     eng = runner.engine
     info = dict(rank=rank, migrations=hook.migrations, losses=losses,
-                layers=len(runner.worker_manager.worker_pool[rank].model_config),
+                # layers on THIS device (the pool is in pipeline order, which the exact allocator
+                # may permute: look the device up, do not index by rank)
+                layers=sum(len(w.model_config) for w in runner.worker_manager.worker_pool
+                           if w.device == rank),
                 fused=bool(eng.in_fused or eng.out_fused), graph=eng._graph is not None,
                 err=eng.fused.error_code() if eng.fused is not None else 0,
                 decision=hook.last_decision)
