@@ -380,6 +380,7 @@ PYBIND11_MODULE(_cuda, m) {
         py::arg("max_ctas") = 0, py::arg("debug") = 0, py::arg("ln_gamma") = 0,
         py::arg("ln_beta") = 0, py::arg("ln_mean") = 0, py::arg("ln_rstd") = 0,
         py::arg("ln_eps") = 1e-12f, py::arg("stream") = 0);
+  m.def("attention_supported", &sky::attention_supported, py::arg("S"), py::arg("head_dim"));
   m.def("gemm_ln_block_n", &sky::gemm_ln_block_n, py::arg("M"), py::arg("N"),
         py::arg("force") = false);
   m.def("gemm_ln_tiles_per_panel", &sky::gemm_ln_tiles_per_panel, py::arg("M"), py::arg("N"),

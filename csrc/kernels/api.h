@@ -129,7 +129,7 @@ int launch_dgelu_mul(const void* g, const void* h, void* y, long long n, cudaStr
 int launch_colsum(const void* x_bf16, int M, int N, int ldx, float* out, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------------
-// Attention (S = 128, head_dim = 64), tcgen05
+// Attention (head_dim = 64; S = 128 single-tile kernels, any other S % 8 == 0 tiled), tcgen05
 // ---------------------------------------------------------------------------------------------
 struct AttnArgs {
   const void* qkv = nullptr;   // bf16 [B*S, 3*H]  (Q | K | V), head h at columns h*64
@@ -146,6 +146,10 @@ struct AttnArgs {
 };
 int launch_attention_fwd(const AttnArgs& a, cudaStream_t stream);
 int launch_attention_bwd(const AttnArgs& a, cudaStream_t stream);
+// any S with S % 8 == 0 (flash-style tiling over 128-key blocks; backward = dQ kernel + dK/dV kernel)
+int launch_attention_fwd_tiled(const AttnArgs& a, cudaStream_t stream);
+int launch_attention_bwd_tiled(const AttnArgs& a, cudaStream_t stream);
+bool attention_supported(int S, int head_dim);
 
 // ---------------------------------------------------------------------------------------------
 // Embeddings: word + position + token-type gather, LayerNorm, dropout; and its backward

@@ -19,6 +19,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cstdlib>
+
 #include "api.h"
 #include "launch_util.h"
 #include "sm100_ptx.cuh"
@@ -439,8 +441,20 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
 
 }  // namespace
 
+// S = 128 runs the single-tile kernels of this file; every other length (and S = 128 when
+// SKY_ATTN_TILED=1, for A/B comparisons) the flash-style tiled kernels of attention_tiled_sm100.cu
+static bool force_tiled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("SKY_ATTN_TILED");
+    v = (e != nullptr && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
+
 int launch_attention_fwd(const AttnArgs& a, cudaStream_t stream) {
-  if (a.S != kS || a.head_dim != kD) return 930;
+  if (a.head_dim != kD) return 930;
+  if (a.S != kS || force_tiled()) return launch_attention_fwd_tiled(a, stream);
   if (a.dropout_p > 0.f && a.rng_state == nullptr) return 903;
   const int H = a.heads * kD;
   CUtensorMap tm;
@@ -472,7 +486,8 @@ int launch_attention_fwd(const AttnArgs& a, cudaStream_t stream) {
 }
 
 int launch_attention_bwd(const AttnArgs& a, cudaStream_t stream) {
-  if (a.S != kS || a.head_dim != kD) return 930;
+  if (a.head_dim != kD) return 930;
+  if (a.S != kS || force_tiled()) return launch_attention_bwd_tiled(a, stream);
   if (a.dropout_p > 0.f && a.rng_state == nullptr) return 903;
   if (a.lse == nullptr || a.ctx == nullptr || a.dctx == nullptr) return 931;
   const int H = a.heads * kD;

@@ -1126,6 +1126,23 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t
   return r == CUDA_SUCCESS ? 0 : 1000 + static_cast<int>(r);
 }
 
+// 3D bf16 tensor map (inner, middle, outer) for [outer][middle][inner] data: the attention kernels
+// view the [B * S, C] activations as (C, S, B) so that a 128-row box never crosses a sequence.
+int make_tmap_bf16_3d(CUtensorMap* tm, const void* ptr, uint64_t inner, uint64_t middle,
+                      uint64_t outer, uint64_t ld_middle_elems, uint64_t ld_outer_elems,
+                      uint32_t box_inner, uint32_t box_middle) {
+  PFN_encodeTiled enc = get_encode_fn();
+  if (!enc) return 901;
+  cuuint64_t gdim[3] = {inner, middle, outer};
+  cuuint64_t gstride[2] = {ld_middle_elems * 2, ld_outer_elems * 2};
+  cuuint32_t box[3] = {box_inner, box_middle, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gdim, gstride,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? 0 : 1000 + static_cast<int>(r);
+}
+
 int gemm_pick_block_n(int M, int N) {
   // 256-wide tiles halve B re-reads and give the best tensor-pipe duty cycle; fall back to 128
   // when that would leave most SMs idle or N is small.

@@ -332,8 +332,10 @@ class BertSpan:
         if hidden.dim() != 3 or H % 8 != 0:
             return False
         if self.head is not None:
+            # tcgen05 attention: head size 64, any sequence length that is a multiple of 8 (S = 128
+            # single-tile kernels, everything else flash-style tiles of 128 keys)
             sa = self.head.attention.self
-            if hidden.shape[1] != 128 or sa.attention_head_size != 64:
+            if sa.attention_head_size != 64 or hidden.shape[1] <= 0 or hidden.shape[1] % 8 != 0:
                 return False
         if self.body is not None and self.body.intermediate.dense_act.act_name not in ("gelu", "bias_gelu"):
             return False

@@ -111,7 +111,7 @@ class PipelineEngine(EngineBase):
             if spans:
                 hidden = self._hidden_size(spans[0])
             in_ok, out_ok = self.stage.fused_boundary_support((self.mb_batch, self.seq, hidden))
-            shape_ok = self.seq == 128 and hidden % 64 == 0 and (self.mb_batch * self.seq) % 128 == 0
+            shape_ok = self.seq % 8 == 0 and hidden % 64 == 0 and (self.mb_batch * self.seq) % 128 == 0
             if spans and spans[0].head is not None:
                 shape_ok = shape_ok and spans[0].head.attention.self.attention_head_size == 64
             in_ok, out_ok = in_ok and shape_ok, out_ok and shape_ok

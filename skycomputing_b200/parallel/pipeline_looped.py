@@ -141,7 +141,7 @@ class LoopedPipelineEngine(EngineBase):
                         ok = ok and sp.head.attention.self.attention_head_size == 64
                 in_ok, out_ok = st.fused_boundary_support((self.mb_batch, self.seq, hidden))
                 ok = ok and (in_ok or k == 0) and (out_ok or k == self.total - 1)
-            ok = ok and self.seq == 128 and hidden > 0 and hidden % 64 == 0 and \
+            ok = ok and self.seq % 8 == 0 and hidden > 0 and hidden % 64 == 0 and \
                 (self.mb_batch * self.seq) % 128 == 0
         flags = [None] * dist.get_world_size(self.group)
         dist.all_gather_object(flags, (bool(ok), int(hidden)), group=self.group)

@@ -234,3 +234,18 @@ def test_full_block_with_the_layernorm_fused_into_the_gemm(monkeypatch):
     before = nat.launch_count()
     _run_pair(["BertLayer_Head", "BertLayer_Body", "BertLayer_Tail"], _hidden_inputs(cfg), cfg)
     assert (nat.launch_count() - before) - fused_launches == 2    # two LayerNorm launches gone
+
+
+@pytest.mark.parametrize("S", [64, 256, 384])
+def test_full_block_other_sequence_lengths_stay_native(S):
+    """The reference's attention handles any S <= 512 (scaelum/model/bert_layers.py:254-275);
+    here those lengths run the tiled tcgen05 attention kernels instead of an eager fallback."""
+    from skycomputing_b200.ops import native as nat
+
+    cfg = _cfg()
+    cfg.max_position_embeddings = 512
+    nat.enable_launch_counter()
+    before = nat.launch_count()
+    _run_pair(["BertLayer_Head", "BertLayer_Body", "BertLayer_Tail"],
+              _hidden_inputs(cfg, B=2, S=S), cfg)
+    assert nat.launch_count() - before >= 20      # the fused span ran (no eager per-layer path)
