@@ -628,8 +628,10 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
 
   tcgen05_fence_after();
   const int key = kt * kT + tid;
-  if (key < p.S) {
-    __nv_bfloat16* grow = p.dqkv + (static_cast<long long>(b) * p.S + key) * (3 * p.H) + h * kD;
+  {
+    // tcgen05.ld is warp-collective (.sync.aligned): every lane loads, only rows of real keys store
+    __nv_bfloat16* grow =
+        p.dqkv + (static_cast<long long>(b) * p.S + (key < p.S ? key : 0)) * (3 * p.H) + h * kD;
 #pragma unroll
     for (int t = 0; t < 2; ++t) {   // t = 0: dK -> K section, t = 1: dV -> V section
       float o[64];
@@ -641,7 +643,7 @@ attention_bwd_dkv_kernel(const __grid_constant__ CUtensorMap tmap_qkv,
 #pragma unroll
         for (int u = 0; u < 32; ++u) o[c * 32 + u] = __uint_as_float(v[u]);
       }
-      store_row64(grow + (t + 1) * p.H, o, 1.f);
+      if (key < p.S) store_row64(grow + (t + 1) * p.H, o, 1.f);
     }
   }
   tcgen05_fence_before();
