@@ -58,7 +58,8 @@ def test_schedule_x_transport_matrix(world):
     if N_GPU < world:
         pytest.skip(f"needs {world} GPUs")
     layers = 2 * world
-    common = ("--layers", str(layers), "--micro-batches", str(world))
+    # 8 sequences (1024 tokens) per micro-batch at every world size
+    common = ("--layers", str(layers), "--micro-batches", str(world), "--batch", str(8 * world))
     runs = {
         "1f1b/nccl": _run(world, "--boundary", "nccl", *common),
         "1f1b/fused": _run(world, "--boundary", "fused", *common),
