@@ -222,6 +222,11 @@ def pick_plan(args) -> dict:
     N = args.gpus
     global_batch = BATCH_PER_GPU * N
     blocks_per_stage = max(1, args.layers // N)
+    if args.slow_rank >= 0 and args.slowdown > 0 and args.alloc != "even":
+        # heterogeneous devices: every GPU runs exactly v chunks of >= 1 block, so the allocator
+        # can only shed work from a slow GPU if v leaves it room (v = blocks per GPU would pin
+        # every GPU to its even share)
+        blocks_per_stage = max(1, int(blocks_per_stage / (2.0 + args.slowdown)) or 1)
     single_gpu_step = 11.7e-3 * args.layers / 24.0      # measured: BENCH_r01 (32 sequences)
     planner = SchedulePlanner(N, costs_from_single_gpu_step(single_gpu_step, N), blocks_per_stage)
     sizes = (args.micro_batch,) if args.micro_batch else (16, 32)
