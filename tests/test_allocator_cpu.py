@@ -288,3 +288,40 @@ def test_schedule_planner_reproduces_measured_steps_and_ranks_plans():
     # one GPU: no pipeline terms, no looped candidates
     p1 = sky.SchedulePlanner(1, sky.costs_from_single_gpu_step(11.72e-3, 1), blocks_per_stage=24)
     assert p1.best(32).virtual_stages == 1 and p1.step_time(32, 1) == pytest.approx(11.72e-3)
+
+
+def test_looped_allocation_balances_device_sums_not_only_chunks():
+    """v chunks per device: the exact solver minimises the most expensive CHUNK; throughput is set
+    by the busiest DEVICE (sum of its chunks).  One 2.2x-slow device out of four, 24 equal blocks,
+    v = 2: the chunk-level optimum leaves a fast device with 8 blocks while the slow one has 2;
+    the refinement moves a block over (max device load 8.0 -> 7.05)."""
+    from skycomputing_b200 import _core
+    from skycomputing_b200.dynamics.allocator import Allocator
+
+    D, v = 4, 2
+    VP = D * v
+    uf = [1.05] + [1.0] * 22 + [1.02]
+    um = [1.0] * 24
+    dt = [1.0, 2.2, 1.0, 1.0]
+    dm = [1e9] * D
+
+    def loads(b):
+        return [sum(sum(uf[b[k]:b[k + 1]]) * dt[k % D] for k in range(d, VP, D)) for d in range(D)]
+
+    res = _core.optimal_partition(uf, um, [dt[k % D] for k in range(VP)],
+                                  [dm[k % D] / v for k in range(VP)], permute=False, min_layers=1,
+                                  cut_penalty=[])
+    b0 = list(res["boundaries"])
+    b1 = Allocator._refine_device_loads(list(b0), uf, um, dt, dm, D)
+    assert max(loads(b1)) < max(loads(b0)) - 0.5
+    assert max(loads(b1)) == pytest.approx(7.05, abs=0.02)
+    assert b1[0] == 0 and b1[-1] == 24 and all(b1[k + 1] > b1[k] for k in range(VP))
+    # homogeneous devices: nothing to refine
+    res = _core.optimal_partition(uf, um, [1.0] * VP, [dm[0] / v] * VP, permute=False, min_layers=1,
+                                  cut_penalty=[])
+    assert Allocator._refine_device_loads(list(res["boundaries"]), uf, um, [1.0] * D, dm, D) == \
+        list(res["boundaries"])
+    # memory caps are respected: a cap that forbids any growth of device 1 keeps its chunks
+    tight = [1e9, 2.0, 1e9, 1e9]
+    b2 = Allocator._refine_device_loads(list(b0), uf, um, dt, tight, D)
+    assert sum(b2[k + 1] - b2[k] for k in range(1, VP, D)) <= 2
