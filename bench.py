@@ -188,7 +188,7 @@ def measure_b1(args, world, rank) -> dict:
             try:
                 proc = subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
                                         text=True, env=env, start_new_session=True)
-                stdout, _ = proc.communicate(timeout=240)
+                stdout, _ = proc.communicate(timeout=150)
                 line = [l for l in stdout.splitlines() if l.startswith("{")][-1]
                 out[dtype] = json.loads(line)
             except subprocess.TimeoutExpired:
@@ -196,7 +196,7 @@ def measure_b1(args, world, rank) -> dict:
 
                 os.killpg(proc.pid, signal.SIGKILL)      # the session we started, nothing else
                 proc.wait()
-                out[dtype] = {"unavailable": "B1 timed out after 240 s"}
+                out[dtype] = {"unavailable": "B1 timed out after 150 s"}
             except Exception as e:
                 out[dtype] = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
             port += 1
