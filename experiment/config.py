@@ -87,6 +87,9 @@ allocator_config = dict(
     type=ALLOCATE_TYPE,
     granularity=os.getenv("GRANULARITY", "block"),
     solver=os.getenv("SOLVER", "heuristic"),
+    # COMM_AWARE=1: charge every cut boundary-bytes / link bandwidth (sizes from the model
+    # benchmarker); matters at GRANULARITY=layer, where a cut after BertLayer_Body ships 5x
+    comm_aware=os.getenv("COMM_AWARE", "0") == "1",
     # VIRTUAL_STAGES=v > 1: looped pipeline, every worker runs v non-adjacent chunks of the model
     # (pipeline fill / drain shrink by v; parallel/pipeline_looped.py)
     virtual_stages=int(os.getenv("VIRTUAL_STAGES", "1")),
@@ -95,7 +98,7 @@ allocator_config = dict(
                    data_generator_cfg=dict(generator_type="DataloaderGenerator",
                                            generator_cfg=data_config)),
         device=dict(
-            # proxy="bert_block": C++ loop over the real tcgen05 GEMM chain (GPU only);
+            # proxy="bert_block": C++ loop over the block's real forward + backward kernels (GPU only);
             # proxy="model": the reference's Conv2d stack (parity, also works on CPU)
             proxy=os.getenv("BENCH_PROXY", "bert_block" if _use_cuda else "model"),
             model_config=[dict(layer_type="Conv2d", in_channels=256 if not TINY else 8,

@@ -98,6 +98,11 @@ class Allocator:
         dm = [float(results[n]["avai_mem"]) for n in names]
         lf, lm = self._model_benchmarker.benchmark()
         lf, lm = [float(x) for x in lf], [float(x) for x in lm]
+        if self._comm_aware and self._boundary_bytes is None:
+            # `comm_aware=True` without explicit sizes: the model benchmarker knows what every
+            # layer hands to the next one (a cut after BertLayer_Body ships 5x the bytes of a cut
+            # after Head / Tail: [M, I] + [M, H] instead of [M, H])
+            self._boundary_bytes = getattr(self._model_benchmarker, "last_boundary_bytes", None)
         # kept for diagnostics / ReallocateHook: benchmark time per PHYSICAL device (stable across
         # re-orderings of the pool, unlike the rank-derived worker names) and the layer costs
         pool = list(self._worker_manager.worker_pool)

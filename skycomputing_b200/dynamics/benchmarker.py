@@ -130,6 +130,9 @@ class ModelBenchmarker(BaseBenchmarker):
     def __init__(self, model_config: list, data_generator, device: str = "cpu",
                  dtype: Optional[str] = None, param_scale: int = 2, analytic: bool = False):
         self._analytic = analytic
+        # stage boundaries carry bf16 on the native path (fp32 in the eager oracle / reference)
+        self._boundary_elem_bytes = 2 if torch.cuda.is_available() else 4
+        self._prev_out_bytes = 0.0
         self._model_config = model_config
         self._data_generator = data_generator
         self._device = device
@@ -147,6 +150,9 @@ class ModelBenchmarker(BaseBenchmarker):
 
     def benchmark(self):
         flops_list, mem_list = [], []
+        # bytes_in[i] = what crosses a stage boundary placed IN FRONT of layer i (the floating
+        # outputs of layer i - 1): feeds the allocator's comm-aware cut penalty
+        self.last_boundary_bytes: List[float] = []
         data = self._data_generator.generate()
         cache: Dict[tuple, tuple] = {}
         for layer_cfg in self._model_config:
@@ -175,4 +181,10 @@ class ModelBenchmarker(BaseBenchmarker):
                 data = outs
             flops_list.append(flops)
             mem_list.append(mem)
+            # payload in front of this layer = what the previous layer produced (set below)
+            self.last_boundary_bytes.append(getattr(self, "_prev_out_bytes", 0.0))
+            self._prev_out_bytes = float(sum(
+                d.numel() * self._boundary_elem_bytes for d in data
+                if torch.is_tensor(d) and d.is_floating_point()))
+        self._prev_out_bytes = 0.0
         return flops_list, mem_list

@@ -325,3 +325,51 @@ def test_looped_allocation_balances_device_sums_not_only_chunks():
     tight = [1e9, 2.0, 1e9, 1e9]
     b2 = Allocator._refine_device_loads(list(b0), uf, um, dt, tight, D)
     assert sum(b2[k + 1] - b2[k] for k in range(1, VP, D)) <= 2
+
+
+def test_comm_aware_allocation_avoids_the_after_body_cut():
+    """at layer granularity a cut after BertLayer_Body ships [M, I] + [M, H]
+    (5x the bytes of a cut after Head / Tail).  `comm_aware=True` takes the boundary sizes from the
+    model benchmarker and charges bytes / link bandwidth per cut; the plain allocator does not care."""
+    import skycomputing_b200 as sky
+    from skycomputing_b200.models import BertConfig
+
+    c = BertConfig(1000, hidden_size=1024, num_hidden_layers=2, num_attention_heads=16,
+                   intermediate_size=4096, max_position_embeddings=128)
+    enc = [dict(layer_type="BertLayer_Head", config=c.__dict__),
+           dict(layer_type="BertLayer_Body", config=c.__dict__),
+           dict(layer_type="BertLayer_Tail", config=c.__dict__)]
+    # Head | Body | Tail with a second, lighter block so that the flop-balanced cut of two equal
+    # devices falls right after the first Body
+    cfg = [dict(layer_type="BertEmbeddings", config=c.__dict__)] + enc + enc[:1]
+
+    class Dev:
+        def __init__(self, wm):
+            self.wm = wm
+
+        def benchmark(self):
+            from skycomputing_b200.utils import generate_worker_name
+
+            return {generate_worker_name(w.rank): dict(time=1.0, avai_mem=1e12)
+                    for w in self.wm.worker_pool}
+
+    def split(comm_aware):
+        wm = sky.WorkerManager(first_rank=0)
+        wm.load_worker_pool_from_config([dict(name=f"w{i}", server_config={}, extra_config={})
+                                         for i in range(2)])
+        gen = sky.build_data_generator("DataloaderGenerator", generator_cfg=dict(
+            dataset_cfg=dict(type="SynthMNLIDataset", num_samples=32, max_seq_length=128),
+            dataloader_cfg=dict(batch_size=32)))
+        mb = sky.ModelBenchmarker(cfg, gen, device="cpu", analytic=True)
+        alloc = sky.Allocator(cfg, wm, mb, Dev(wm), solver="exact", granularity="layer",
+                              comm_aware=comm_aware, link_bytes_per_s=340e9,
+                              device_flops_per_s=7e14)
+        wm = alloc.optimal_allocate(permute=False)
+        return [len(w.model_config) for w in wm.worker_pool], mb.last_boundary_bytes
+
+    plain, sizes = split(False)
+    aware, _ = split(True)
+    # boundary in front of Tail (= after Body) is 5x the one in front of Body (= after Head)
+    assert sizes[3] == pytest.approx(5 * sizes[2], rel=0.01) and sizes[0] == 0.0
+    assert plain == [3, 2]                    # emb, Head, Body | Tail, Head: flop-balanced
+    assert aware in ([2, 3], [4, 1])          # the 80 MiB cut is avoided
