@@ -73,7 +73,7 @@ class Runner:
         self.parameter_server = parameter_server
         self.optimizer = optimizer
         self._hooks = []
-        self._hook_impl = []
+        self._hook_impl = {}
         self._fixed_batch = None
         self._epoch = 0
         self._iter = 0
@@ -190,12 +190,16 @@ class Runner:
     def register_hook(self, hook: Hook) -> None:
         assert isinstance(hook, Hook)
         self._hooks.append(hook)
-        self._hook_impl.append(type(hook).overrides())
 
     def _call_hook(self, fn_name: str) -> None:
-        # hooks that do not implement `fn_name` are skipped without a Python call
-        for hook, impl in zip(self._hooks, self._hook_impl):
-            if fn_name in impl:
+        # hooks whose class does not implement `fn_name` are skipped without a Python call (the
+        # set of implemented callbacks is computed once per hook class; hooks appended to
+        # `runner.hooks` directly are handled the same way)
+        for hook in self._hooks:
+            impl = self._hook_impl.get(type(hook))
+            if impl is None:
+                impl = self._hook_impl[type(hook)] = type(hook).overrides()
+            if fn_name in impl or fn_name in getattr(hook, "__dict__", ()):
                 hook.fire(self, fn_name)
 
     def _log(self, msg: str) -> None:
