@@ -104,6 +104,20 @@ class BackwardSlowdownModule(nn.Module):
                                               self.logger, self.do_slowdown)
 
 
+def _in_fusable(span) -> bool:
+    """Can this span consume its input from a fused peer slot?  Yes when it starts a block (Head:
+    QKV GEMM gated on the panel flags) or starts at Body (cut after BertLayer_Head: the FFN1 GEMM
+    is gated, attn_out doubles as the residual of Tail); not when it starts at Tail (cut after
+    Body: two tensors, 5x the bytes - stays on torch.distributed p2p)."""
+    return span.head is not None or span.body is not None
+
+
+def _out_fusable(span) -> bool:
+    """Can this span write its output into the next stage's HBM?  When it ends a block (Tail:
+    FFN2 GEMM + LayerNorm) or is Head alone (attention-output GEMM + LayerNorm)."""
+    return span.tail is not None or (span.head is not None and span.body is None)
+
+
 class ModuleWrapper(nn.Module):
     def __init__(
         self,
@@ -231,8 +245,12 @@ class ModuleWrapper(nn.Module):
             if isinstance(step, BertSpan):
                 hidden = inputs[0] if step.head is not None or step.body is not None else inputs[1]
                 if step.supports(hidden):
-                    step.in_channel = self.in_channel if (idx == 0 and step.head is not None) else None
-                    step.out_channel = self.out_channel if (idx == n - 1 and step.tail is not None) else None
+                    # fusable cuts: in front of a block (span starts with Head) or after
+                    # BertLayer_Head (span starts with Body: attn_out arrives in the slot, FFN1 is
+                    # the flag-gated consumer); behind a block (span ends with Tail) or after Head
+                    # (Head-only span: the K4 GEMM + LayerNorm writes the peer slot)
+                    step.in_channel = self.in_channel if (idx == 0 and _in_fusable(step)) else None
+                    step.out_channel = self.out_channel if (idx == n - 1 and _out_fusable(step)) else None
                     step.microbatch = self.microbatch
                     inputs = step(*inputs)
                 else:
@@ -254,8 +272,8 @@ class ModuleWrapper(nn.Module):
         from ..models.bert_layers import BertSpan
 
         first, last = self._plan[0], self._plan[-1]
-        in_ok = isinstance(first, BertSpan) and first.head is not None
-        out_ok = isinstance(last, BertSpan) and last.tail is not None
+        in_ok = isinstance(first, BertSpan) and _in_fusable(first)
+        out_ok = isinstance(last, BertSpan) and _out_fusable(last)
         if shape is not None and shape[0] and shape[1] and shape[2]:
             probe = torch.empty(tuple(shape), device="meta")
             in_ok = in_ok and first.supports(probe)

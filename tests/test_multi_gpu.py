@@ -107,3 +107,18 @@ def test_reallocation_rebuilds_fused_engine_on_gpus():
     assert r["layers_after"][0] > r["layers_before"][0] and r["layers_after"][1] < r["layers_before"][1]
     assert r["fused_after"] and r["graph_after"]
     assert all(l == l and l < 20 for l in r["losses"])
+
+
+@pytest.mark.skipif(N_GPU < 2, reason="needs two GPUs")
+def test_cut_after_bert_layer_head_is_fused_too():
+    """The reference's layer granularity: 4 blocks on 2 GPUs split 8 | 7 list entries, i.e. right
+    after a BertLayer_Head.  The attention-output GEMM (+ LayerNorm) writes the peer slot, the
+    FFN1 GEMM of the next stage is the flag-gated consumer, the FFN1 dgrad returns the gradient:
+    same single-graph step, same losses as the NCCL pipeline with whole-block cuts."""
+    nccl = _run(2, "--boundary", "nccl")
+    fused = _run(2, "--boundary", "fused", "--granularity", "layer")
+    assert fused["layers"] == [8, 7]
+    assert fused["fused_any"] and fused["graph_all"] and fused["err_any"] == 0
+    assert fused["losses"][0] == nccl["losses"][0]
+    for a, b in zip(fused["losses"], nccl["losses"]):
+        assert a == pytest.approx(b, rel=3e-3, abs=3e-3)

@@ -179,3 +179,23 @@ def test_fused_boundary_support_evaluates_span_supports():
     relu = stage("relu")
     assert relu.fused_boundary_support() == (True, True)              # structurally a whole block
     assert relu.fused_boundary_support((4, 128, 64)) == (False, False)
+
+
+def test_fused_boundary_support_covers_the_cut_after_head():
+    """Layer granularity (the reference's): a stage may end with BertLayer_Head alone (the K4
+    GEMM + LayerNorm writes the peer slot) and the next one start with BertLayer_Body (FFN1 is the
+    flag-gated consumer); a cut after BertLayer_Body (two tensors, 5x the bytes) is not fused."""
+    from skycomputing_b200.models import BertConfig
+
+    c = BertConfig(100, hidden_size=64, num_hidden_layers=1, num_attention_heads=1,
+                   intermediate_size=128, max_position_embeddings=128)
+    H, B, T = (dict(layer_type=f"BertLayer_{n}", config=c.__dict__) for n in ("Head", "Body", "Tail"))
+
+    def support(layers):
+        st = sky.build_module_from_cfg(0, layers, dict(module_to_cuda=False))
+        return st.fused_boundary_support((4, 128, 64))
+
+    assert support([H, B, T, H]) == (True, True)          # ... | Head   ends after Head
+    assert support([B, T, H, B, T]) == (True, True)       # Body ...     starts after Head
+    assert support([H, B]) == (True, False)               # ends after Body: not fused
+    assert support([T, H, B, T]) == (False, True)         # starts after Body: not fused

@@ -28,6 +28,8 @@ def main():
     # > 1: looped pipeline (v chunks per GPU); add SKY_LOOPED_FUSED=1 for its fused ring boundary.
     # The loss trajectory must equal the plain pipeline's (same seeds per GLOBAL layer index).
     ap.add_argument("--virtual-stages", type=int, default=1)
+    # "layer": the reference's granularity (cuts may fall after BertLayer_Head / Body)
+    ap.add_argument("--granularity", default="block", choices=["block", "layer"])
     a = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -53,7 +55,7 @@ def main():
                for i in range(world)]
     wm = sky.WorkerManager(first_rank=0)
     wm.load_worker_pool_from_config(workers)
-    wm = sky.Allocator(model_config, wm, granularity="block").allocate(
+    wm = sky.Allocator(model_config, wm, granularity=a.granularity).allocate(
         "even", virtual_stages=a.virtual_stages)
     # identical initial weights regardless of the partition: seed per GLOBAL layer index
     model = sky.RpcModel(wm, this_rank=rank)
@@ -88,6 +90,7 @@ def main():
     eng = runner.engine
     info = dict(tag=a.tag, world=world, boundary=a.boundary, schedule=eng.schedule,
                 virtual_stages=a.virtual_stages, fused=(eng.in_fused or eng.out_fused),
+                layers=[len(w.model_config) for w in wm.worker_pool],
                 graph=eng._graph is not None, mb=a.micro_batches, losses=losses,
                 err=eng.fused.error_code() if eng.fused is not None else 0)
     gathered = [None] * world
