@@ -224,7 +224,8 @@ def test_hook_base_helpers():
 def test_span_fusion_plan_and_boundary_support(tmp_path):
     """ModuleWrapper groups consecutive Head / Body / Tail entries into fused spans (one autograd
     node, one kernel chain) whatever sub-block cut the allocator chose, and reports which sides of
-    the stage can use the fused NVLink boundary (whole-block cuts only)."""
+    the stage can use the fused NVLink boundary (whole-block cuts and the cut after
+    BertLayer_Head; a cut after BertLayer_Body ships two tensors and stays on p2p)."""
     from skycomputing_b200.models.bert_layers import BertSpan
 
     c = sky.BertConfig(50, hidden_size=32, num_hidden_layers=2, num_attention_heads=4,
@@ -249,7 +250,7 @@ def test_span_fusion_plan_and_boundary_support(tmp_path):
     assert shape([L("BertEmbeddings"), H, B, T, H, B, T] + tail_cls) == (
         ["BertEmbeddings", "HBT", "HBT", "BertPooler", "BertTailForClassification"], (False, False), 2)
     assert shape([H, B, T, H, B, T]) == (["HBT", "HBT"], (True, True), 2)       # middle stage
-    assert shape([B, T, H, B]) == (["BT", "HB"], (False, False), 2)             # sub-block cuts
-    assert shape([T, H]) == (["T", "H"], (False, False), 2)
+    assert shape([B, T, H, B]) == (["BT", "HB"], (True, False), 2)   # starts after Head (fusable), ends after Body (not)
+    assert shape([T, H]) == (["T", "H"], (False, True), 2)           # starts after Body (not), ends after Head (fusable)
     assert shape([H, B, T] + tail_cls)[1] == (True, False)                       # last stage
     assert shape([L("BertEmbeddings"), H, B, T])[1] == (False, True)             # first stage
