@@ -199,3 +199,34 @@ def test_fused_boundary_support_covers_the_cut_after_head():
     assert support([B, T, H, B, T]) == (True, True)       # Body ...     starts after Head
     assert support([H, B]) == (True, False)               # ends after Body: not fused
     assert support([T, H, B, T]) == (False, True)         # starts after Body: not fused
+
+
+def test_bench_plan_picker_matches_the_validated_plans():
+    """bench.py's schedule choice (SchedulePlanner): the plans that were validated on 1 / 2 / 4 / 8
+    GPUs, flag overrides, and slack for the allocator when a device is declared slow."""
+    import argparse
+    import importlib.util
+    import pathlib
+
+    spec = importlib.util.spec_from_file_location(
+        "sky_bench", pathlib.Path(__file__).resolve().parents[1] / "bench.py")
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    def plan(**kw):
+        a = dict(gpus=1, layers=24, micro_batch=0, virtual_stages=0, slow_rank=-1, slowdown=0.0,
+                 alloc="optimal")
+        a.update(kw)
+        return bench.pick_plan(argparse.Namespace(**a))
+
+    assert plan(gpus=1)["schedule"] == "sequential" and plan(gpus=1)["virtual_stages"] == 1
+    for n, v, m in ((2, 6, 2), (4, 6, 4), (8, 3, 8)):
+        p = plan(gpus=n)
+        assert (p["schedule"], p["virtual_stages"], p["micro_batches"], p["micro_batch"]) == \
+            ("looped", v, m, 32), (n, p)
+    assert plan(gpus=8, layers=160)["virtual_stages"] == 10
+    assert plan(gpus=4, virtual_stages=1)["schedule"] == "1f1b"
+    assert plan(gpus=4, micro_batch=16)["micro_batch"] == 16
+    slow = plan(gpus=4, slow_rank=1, slowdown=1.0)
+    assert slow["schedule"] == "looped" and slow["virtual_stages"] <= 2     # room to shed blocks
+    assert plan(gpus=4, slow_rank=1, slowdown=1.0, alloc="even")["virtual_stages"] == 6
