@@ -515,6 +515,11 @@ def main():
     out = run_ours(args)
     if out is not None:
         print(json.dumps(out), flush=True)
+    elif int(os.environ.get("RANK", "0")) == 0:
+        # both the planned schedule and the plain 1F1B fallback failed their warm-up check
+        print(json.dumps({"impl": "ours", "unavailable": "no schedule passed the warm-up health "
+                          "check (flag-wait error or non-finite loss); see stderr"}), flush=True)
+        return 1
     return 0
 
 
