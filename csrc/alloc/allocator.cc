@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <limits>
 #include <numeric>
 #include <stdexcept>
@@ -471,6 +472,88 @@ AllocResult optimal_partition(const AllocProblem& p, bool permute, int min_layer
   r.exact = true;
   r.method = "bisection+subset-dp";
   return r;
+}
+
+// ------------------------------------------------------------------------------------------
+// looped pipelines: balance the per-device sums of a chunk-level partition
+// ------------------------------------------------------------------------------------------
+namespace {
+struct LoopedScore {
+  std::vector<double> sorted_loads;  // descending
+  double worst_chunk = 0.0;
+  std::vector<double> loads;         // per device, unsorted
+  bool feasible = true;
+  bool better_than(const LoopedScore& o) const {
+    if (sorted_loads != o.sorted_loads)
+      return std::lexicographical_compare(sorted_loads.begin(), sorted_loads.end(),
+                                          o.sorted_loads.begin(), o.sorted_loads.end());
+    return worst_chunk < o.worst_chunk;
+  }
+};
+
+LoopedScore looped_score(const std::vector<double>& pre_f, const std::vector<double>& pre_m,
+                         const AllocProblem& p, const std::vector<int>& b) {
+  const int D = static_cast<int>(p.dev_time.size());
+  const int VP = static_cast<int>(b.size()) - 1;
+  LoopedScore s;
+  s.loads.assign(D, 0.0);
+  std::vector<double> mem(D, 0.0);
+  for (int k = 0; k < VP; ++k) {
+    const double c = (pre_f[b[k + 1]] - pre_f[b[k]]) * p.dev_time[k % D];
+    s.loads[k % D] += c;
+    mem[k % D] += pre_m[b[k + 1]] - pre_m[b[k]];
+    s.worst_chunk = std::max(s.worst_chunk, c);
+  }
+  for (int d = 0; d < D; ++d)
+    if (mem[d] > p.dev_mem[d]) s.feasible = false;
+  s.sorted_loads = s.loads;
+  std::sort(s.sorted_loads.begin(), s.sorted_loads.end(), std::greater<double>());
+  return s;
+}
+}  // namespace
+
+std::vector<int> refine_looped_partition(const AllocProblem& p, std::vector<int> b) {
+  const int D = static_cast<int>(p.dev_time.size());
+  const int VP = static_cast<int>(b.size()) - 1;
+  const int L = static_cast<int>(p.layer_flops.size());
+  if (D <= 0 || VP <= 0 || VP % D != 0 || b.front() != 0 || b.back() != L)
+    throw std::invalid_argument("refine_looped_partition: boundaries do not describe v * D chunks");
+  std::vector<double> pre_f(L + 1, 0.0), pre_m(L + 1, 0.0);
+  for (int i = 0; i < L; ++i) {
+    pre_f[i + 1] = pre_f[i] + p.layer_flops[i];
+    pre_m[i + 1] = pre_m[i] + p.layer_mem[i];
+  }
+  LoopedScore cur = looped_score(pre_f, pre_m, p, b);
+  for (int iter = 0; iter < 20 * VP; ++iter) {
+    int busiest = 0;
+    for (int d = 1; d < D; ++d)
+      if (cur.loads[d] > cur.loads[busiest]) busiest = d;
+    bool found = false;
+    LoopedScore best;
+    std::vector<int> best_b;
+    for (int k = busiest; k < VP; k += D) {
+      for (int side = 0; side < 2; ++side) {
+        if (b[k + 1] - b[k] <= 1) continue;
+        std::vector<int> nb = b;
+        if (side == 0 && k > 0)
+          nb[k] += 1;            // first unit of chunk k goes to chunk k - 1
+        else if (side == 1 && k < VP - 1)
+          nb[k + 1] -= 1;        // last unit of chunk k goes to chunk k + 1
+        else
+          continue;
+        LoopedScore sc = looped_score(pre_f, pre_m, p, nb);
+        if (sc.feasible && sc.better_than(cur) && (!found || sc.better_than(best))) {
+          best = sc;
+          best_b = nb;
+          found = true;
+        }
+      }
+    }
+    if (!found) break;
+    cur = best;
+    b = best_b;
+  }
+  return b;
 }
 
 }  // namespace sky

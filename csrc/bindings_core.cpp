@@ -68,6 +68,16 @@ PYBIND11_MODULE(_core, m) {
       },
       py::arg("layer_flops"), py::arg("layer_mem"), py::arg("dev_time"), py::arg("dev_mem"),
       py::arg("order"), py::arg("boundaries"), py::arg("cut_penalty") = std::vector<double>());
+  m.def(
+      "refine_looped_partition",
+      [](const std::vector<double>& lf, const std::vector<double>& lm,
+         const std::vector<double>& dt, const std::vector<double>& dm,
+         const std::vector<int>& boundaries) {
+        return refine_looped_partition(make_problem(lf, lm, dt, dm, {}), boundaries);
+      },
+      py::arg("layer_flops"), py::arg("layer_mem"), py::arg("dev_time"), py::arg("dev_mem"),
+      py::arg("boundaries"),
+      "looped pipelines: refine a v * D chunk partition towards balanced per-device loads");
   m.def("numpy_default_rng_random", &numpy_default_rng_random, py::arg("seed"), py::arg("n"));
   py::class_<Stimulator>(m, "Stimulator")
       .def(py::init<int, uint64_t, uint64_t, uint64_t>(), py::arg("worker_num"),

@@ -233,52 +233,16 @@ class Allocator:
 
     @staticmethod
     def _refine_device_loads(bounds: List[int], uf, um, dt, dm, D: int) -> List[int]:
-        """Hill-climb on the chunk boundaries of a looped partition: repeatedly shrink a chunk of
-        the busiest device by one unit (handing the unit to the neighbouring chunk, which belongs
-        to another device) while that lowers the (descending-sorted) vector of device loads
-        dt[d] x sum(flops of d's chunks); ties are broken towards the smaller most-expensive chunk.  Every chunk keeps >= 1 unit, device
-        memory caps are respected."""
-        VP = len(bounds) - 1
-        pre_f = [0.0]
-        pre_m = [0.0]
-        for f, m_ in zip(uf, um):
-            pre_f.append(pre_f[-1] + f)
-            pre_m.append(pre_m[-1] + m_)
-
-        def score(b):
-            load = [0.0] * D
-            mem = [0.0] * D
-            worst_chunk = 0.0
-            for k in range(VP):
-                c = (pre_f[b[k + 1]] - pre_f[b[k]]) * dt[k % D]
-                load[k % D] += c
-                mem[k % D] += pre_m[b[k + 1]] - pre_m[b[k]]
-                worst_chunk = max(worst_chunk, c)
-            ok = all(mem[d] <= dm[d] for d in range(D))
-            # lexicographic: the sorted device loads (so that un-tying two equally busy devices
-            # counts as progress), then the most expensive chunk
-            return (tuple(sorted(load, reverse=True)), worst_chunk), load, ok
-
-        cur, load, _ = score(bounds)
-        for _ in range(20 * VP):
-            busiest = max(range(D), key=lambda d: load[d])
-            best = None
-            for k in range(busiest, VP, D):
-                for side in (0, 1):
-                    nb = list(bounds)
-                    if side == 0 and k > 0 and nb[k + 1] - nb[k] > 1:
-                        nb[k] += 1              # first unit of chunk k goes to chunk k - 1
-                    elif side == 1 and k < VP - 1 and nb[k + 1] - nb[k] > 1:
-                        nb[k + 1] -= 1          # last unit of chunk k goes to chunk k + 1
-                    else:
-                        continue
-                    sc, ld, ok = score(nb)
-                    if ok and sc < cur and (best is None or sc < best[0]):
-                        best = (sc, nb, ld)
-            if best is None:
-                break
-            cur, bounds, load = best
-        return bounds
+        """Hill-climb on the chunk boundaries of a looped partition (C++ core,
+        csrc/alloc/allocator.cc: refine_looped_partition): repeatedly shrink a chunk of the busiest
+        device by one unit (handing the unit to the neighbouring chunk, which belongs to another
+        device) while that lowers the descending-sorted vector of device loads
+        dt[d] x sum(flops of d's chunks); ties are broken towards the smaller most-expensive
+        chunk.  Every chunk keeps >= 1 unit, device memory caps are respected."""
+        assert len(dt) == D and len(dm) == D
+        return list(_core.refine_looped_partition([float(x) for x in uf], [float(x) for x in um],
+                                                  [float(x) for x in dt], [float(x) for x in dm],
+                                                  [int(x) for x in bounds]))
 
     def allocate(self, alloc_type: str, virtual_stages: int = 1, **kwargs) -> WorkerManager:
         """Dispatch on ``allocator_config['type']`` (experiment/launch.py:119-138 semantics)."""

@@ -373,3 +373,42 @@ def test_comm_aware_allocation_avoids_the_after_body_cut():
     assert sizes[3] == pytest.approx(5 * sizes[2], rel=0.01) and sizes[0] == 0.0
     assert plain == [3, 2]                    # emb, Head, Body | Tail, Head: flop-balanced
     assert aware in ([2, 3], [4, 1])          # the 80 MiB cut is avoided
+
+
+def test_refine_looped_partition_properties_random():
+    """C++ refine_looped_partition on random instances: valid boundaries, every chunk >= 1 unit,
+    memory caps kept, and the (sorted device loads, worst chunk) score never gets worse."""
+    import random
+
+    from skycomputing_b200 import _core
+
+    rnd = random.Random(7)
+    for _ in range(200):
+        D = rnd.randint(2, 5)
+        v = rnd.randint(1, 4)
+        VP = D * v
+        L = rnd.randint(VP, VP + 30)
+        uf = [rnd.uniform(0.1, 3.0) for _ in range(L)]
+        um = [rnd.uniform(0.5, 2.0) for _ in range(L)]
+        dt = [rnd.choice([1.0, 1.0, 1.5, 2.0, 3.0]) for _ in range(D)]
+        cuts = sorted(rnd.sample(range(1, L), VP - 1))
+        b0 = [0] + cuts + [L]
+
+        def stats(b):
+            loads = [sum(sum(uf[b[k]:b[k + 1]]) * dt[k % D] for k in range(d, VP, D)) for d in range(D)]
+            mem = [sum(sum(um[b[k]:b[k + 1]]) for k in range(d, VP, D)) for d in range(D)]
+            worst = max(sum(uf[b[k]:b[k + 1]]) * dt[k % D] for k in range(VP))
+            return loads, mem, worst
+
+        l0, m0, w0 = stats(b0)
+        dm = [x * rnd.choice([1.0, 1.2, 10.0]) for x in m0]       # feasible at the start
+        b1 = list(_core.refine_looped_partition(uf, um, dt, dm, b0))
+        assert b1[0] == 0 and b1[-1] == L and len(b1) == VP + 1
+        assert all(b1[k + 1] - b1[k] >= 1 for k in range(VP))
+        l1, m1, w1 = stats(b1)
+        assert all(m1[d] <= dm[d] + 1e-9 for d in range(D))
+        s0 = (tuple(sorted(l0, reverse=True)), w0)
+        s1 = (tuple(sorted(l1, reverse=True)), w1)
+        assert s1 <= s0
+    with pytest.raises(Exception):
+        _core.refine_looped_partition([1.0] * 4, [1.0] * 4, [1.0, 1.0], [9.0, 9.0], [0, 2, 3])
